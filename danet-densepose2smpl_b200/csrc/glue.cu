@@ -1,0 +1,610 @@
+// Memory-bound fp32 glue kernels of the DaNet network half (NHWC activations).
+// Each replaces a chain of small ATen launches in the reference; citations per kernel.
+#include "common.cuh"
+#include <math.h>
+
+namespace danet {
+
+// utils/smpl_utlis.py:13-17,29-53 (structure tables used by iuv_estimator.py:176-184,262-301)
+__constant__ int c_parents0[24] = {0, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 20, 21};
+__constant__ int c_children1[24] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 10, 11, 15, 16, 17, 15, 18, 19, 20, 21, 22, 23, 22, 23};
+// smpl2dp_part as 25-bit masks over DensePose part ids
+__constant__ unsigned c_part_mask[24] = {
+    (1u << 1) | (1u << 2), (1u << 8) | (1u << 10), (1u << 7) | (1u << 9), (1u << 1) | (1u << 2),
+    (1u << 8) | (1u << 10) | (1u << 12) | (1u << 14), (1u << 7) | (1u << 9) | (1u << 11) | (1u << 13),
+    (1u << 1) | (1u << 2), (1u << 12) | (1u << 14) | (1u << 5), (1u << 11) | (1u << 13) | (1u << 6),
+    (1u << 1) | (1u << 2), (1u << 12) | (1u << 14) | (1u << 5), (1u << 11) | (1u << 13) | (1u << 6),
+    (1u << 1) | (1u << 2) | (1u << 23) | (1u << 24), (1u << 15) | (1u << 17), (1u << 16) | (1u << 18),
+    (1u << 23) | (1u << 24), (1u << 15) | (1u << 17), (1u << 16) | (1u << 18),
+    (1u << 15) | (1u << 17) | (1u << 19) | (1u << 21), (1u << 16) | (1u << 18) | (1u << 20) | (1u << 22),
+    (1u << 19) | (1u << 21) | (1u << 4), (1u << 20) | (1u << 22) | (1u << 3),
+    (1u << 19) | (1u << 21) | (1u << 4), (1u << 20) | (1u << 22) | (1u << 3)};
+
+// torch.argmax semantics: first maximal value; NaN counts as maximal
+__device__ __forceinline__ int argmax_first(const float* v, int n) {
+    int best = 0; float bv = v[0];
+    for (int c = 1; c < n; ++c) {
+        const float x = v[c];
+        if ((x > bv) || (x != x && bv == bv)) { bv = x; best = c; }
+    }
+    return best;
+}
+
+// ------------------------------------------------------------------------------------------
+// NCHW image -> NHWC padded (input boundary of the network; demo.py:106 / eval.py:147 tensors)
+// ------------------------------------------------------------------------------------------
+__global__ void k_nchw_to_nhwc(int N, int C, int HW, int Cp, const float* __restrict__ x, float* __restrict__ y) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)N * HW) return;
+    const int n = (int)(i / HW), p = (int)(i % HW);
+    for (int c = 0; c < Cp; ++c) y[i * Cp + c] = c < C ? x[((size_t)n * C + c) * HW + p] : 0.0f;
+}
+
+// ------------------------------------------------------------------------------------------
+// iuvmap_clean, global heads (utils/iuvmap.py:6-38 via danet.py:79 / iuv_estimator.py:127)
+// ------------------------------------------------------------------------------------------
+__global__ void k_iuv_clean_global(int B, int HW, int Chead, int off_u, int off_v, int off_i, int off_a,
+                                   int Cb, const float* __restrict__ heads, float* __restrict__ body,
+                                   uint8_t* __restrict__ amax, float* un, float* vn, float* in_, float* an) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * HW) return;
+    const int b = i / HW, pix = i % HW;
+    const float* h = heads + (size_t)i * Chead;
+    float I[25], A[15];
+#pragma unroll
+    for (int c = 0; c < 25; ++c) I[c] = h[off_i + c];
+    const int best = argmax_first(I, 25);
+    amax[i] = (uint8_t)best;
+    float* o = body + (size_t)i * Cb;
+    for (int c = 0; c < 25; ++c) {
+        const float oh = (c == best) ? 1.0f : 0.0f;
+        const float u = oh * h[off_u + c], v = oh * h[off_v + c];
+        o[c] = u; o[25 + c] = v; o[50 + c] = oh;
+        if (un) un[((size_t)b * 25 + c) * HW + pix] = u;
+        if (vn) vn[((size_t)b * 25 + c) * HW + pix] = v;
+        if (in_) in_[((size_t)b * 25 + c) * HW + pix] = oh;
+    }
+    for (int c = 75; c < Cb; ++c) o[c] = 0.0f;
+    if (an) {
+#pragma unroll
+        for (int c = 0; c < 15; ++c) A[c] = h[off_a + c];
+        const int ba = argmax_first(A, 15);
+        for (int c = 0; c < 15; ++c) an[((size_t)b * 15 + c) * HW + pix] = (c == ba) ? 1.0f : 0.0f;
+    }
+}
+
+// 24 per-part iuvmap_clean calls of danet.py:93-98 in one pass
+__global__ void k_iuv_clean_parts(int N, int HW, int Cx, int Cy, const float* __restrict__ x,
+                                  float* __restrict__ y, float* raw) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)N * HW) return;
+    const float* h = x + i * Cx;
+    float v[21];
+#pragma unroll
+    for (int c = 0; c < 21; ++c) v[c] = h[c];
+    const int best = argmax_first(v + 14, 7);
+    float* o = y + i * Cy;
+#pragma unroll
+    for (int c = 0; c < 7; ++c) {
+        const float oh = (c == best) ? 1.0f : 0.0f;
+        o[c] = oh * v[c]; o[7 + c] = oh * v[7 + c]; o[14 + c] = oh;
+    }
+    for (int c = 21; c < Cy; ++c) o[c] = 0.0f;
+    if (raw) {
+        const size_t n = i / HW, pix = i % HW;
+#pragma unroll
+        for (int c = 0; c < 21; ++c) raw[(n * 21 + c) * HW + pix] = v[c];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// soft-argmax centres + part visibility + affine thetas
+// (utils/keypoints.py:372-394, iuv_estimator.py:137-140,176-184,262-301)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float bilinear_point(const uint8_t* amax, int S, unsigned mask, float gx, float gy,
+                                                int align_corners) {
+    float ix, iy;
+    if (align_corners) { ix = (gx + 1.0f) * 0.5f * (float)(S - 1); iy = (gy + 1.0f) * 0.5f * (float)(S - 1); }
+    else { ix = ((gx + 1.0f) * (float)S - 1.0f) * 0.5f; iy = ((gy + 1.0f) * (float)S - 1.0f) * 0.5f; }
+    const float fx = floorf(ix), fy = floorf(iy);
+    const int x0 = (int)fx, y0 = (int)fy;
+    const float tx = ix - fx, ty = iy - fy;
+    float acc = 0.0f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+            const int xx = x0 + dx, yy = y0 + dy;
+            if (xx < 0 || xx >= S || yy < 0 || yy >= S) continue;
+            const float val = ((mask >> amax[yy * S + xx]) & 1u) ? 1.0f : 0.0f;
+            acc += val * (dx ? tx : 1.0f - tx) * (dy ? ty : 1.0f - ty);
+        }
+    return acc;
+}
+
+constexpr int kStnThreads = 256;
+
+__global__ void __launch_bounds__(kStnThreads)
+k_stn_params(int B, int S, int Chm, const float* __restrict__ hm, const uint8_t* __restrict__ amax,
+             const float* __restrict__ ratio, const float* __restrict__ offset, float vis_thresh,
+             int align_corners, float* __restrict__ centers, float* __restrict__ theta) {
+    __shared__ float s_red[kStnThreads / 32][24 * 3];
+    __shared__ float s_max[24];
+    __shared__ float s_c[24][2];
+    const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int HW = S * S;
+    const float* h = hm + (size_t)b * HW * Chm;
+    // pass 1: per-joint max of 10*hm
+    float mx[24];
+#pragma unroll
+    for (int j = 0; j < 24; ++j) mx[j] = -INFINITY;
+    for (int p = tid; p < HW; p += kStnThreads) {
+        const float4* r = reinterpret_cast<const float4*>(h + (size_t)p * Chm);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            const float4 v = r[q];
+            mx[q * 4 + 0] = fmaxf(mx[q * 4 + 0], 10.0f * v.x); mx[q * 4 + 1] = fmaxf(mx[q * 4 + 1], 10.0f * v.y);
+            mx[q * 4 + 2] = fmaxf(mx[q * 4 + 2], 10.0f * v.z); mx[q * 4 + 3] = fmaxf(mx[q * 4 + 3], 10.0f * v.w);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 24; ++j) { const float m = warp_max(mx[j]); if (lane == 0) s_red[warp][j] = m; }
+    __syncthreads();
+    if (tid < 24) {
+        float m = s_red[0][tid];
+        for (int w = 1; w < kStnThreads / 32; ++w) m = fmaxf(m, s_red[w][tid]);
+        s_max[tid] = m;
+    }
+    __syncthreads();
+    // pass 2: sum exp, sum exp*x, sum exp*y
+    float se[24], sx[24], sy[24];
+#pragma unroll
+    for (int j = 0; j < 24; ++j) { se[j] = 0.f; sx[j] = 0.f; sy[j] = 0.f; mx[j] = s_max[j]; }
+    for (int p = tid; p < HW; p += kStnThreads) {
+        const float px = (float)(p % S), py = (float)(p / S);
+        const float* r = h + (size_t)p * Chm;
+#pragma unroll
+        for (int j = 0; j < 24; ++j) {
+            const float e = expf(10.0f * r[j] - mx[j]);
+            se[j] += e; sx[j] = fmaf(e, px, sx[j]); sy[j] = fmaf(e, py, sy[j]);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 24; ++j) {
+        const float a = warp_sum(se[j]), bx = warp_sum(sx[j]), by = warp_sum(sy[j]);
+        if (lane == 0) { s_red[warp][j * 3] = a; s_red[warp][j * 3 + 1] = bx; s_red[warp][j * 3 + 2] = by; }
+    }
+    __syncthreads();
+    if (tid < 24) {
+        float a = 0.f, bx = 0.f, by = 0.f;
+        for (int w = 0; w < kStnThreads / 32; ++w) { a += s_red[w][tid * 3]; bx += s_red[w][tid * 3 + 1]; by += s_red[w][tid * 3 + 2]; }
+        // stn_centers = softargmax / (0.5*S) - 1  (iuv_estimator.py:137-140)
+        const float cx = (bx / a) / (0.5f * (float)S) - 1.0f;
+        const float cy = (by / a) / (0.5f * (float)S) - 1.0f;
+        s_c[tid][0] = cx; s_c[tid][1] = cy;
+        centers[((size_t)b * 24 + tid) * 2] = cx;
+        centers[((size_t)b * 24 + tid) * 2 + 1] = cy;
+    }
+    __syncthreads();
+    if (tid < 24) {
+        const int i = tid;
+        float xmin = s_c[0][0], xmax = xmin, ymin = s_c[0][1], ymax = ymin;
+        for (int j = 1; j < 24; ++j) {
+            xmin = fminf(xmin, s_c[j][0]); xmax = fmaxf(xmax, s_c[j][0]);
+            ymin = fminf(ymin, s_c[j][1]); ymax = fmaxf(ymax, s_c[j][1]);
+        }
+        const float scale_box = fmaxf(xmax - xmin, ymax - ymin) / 2.0f;
+        float scale;
+        if (i == 0) {
+            scale = scale_box;
+        } else {
+            const int pi = c_parents0[i], ci = c_children1[i];
+            const float dcx = s_c[ci][0] - s_c[i][0], dcy = s_c[ci][1] - s_c[i][1];
+            const float dpx = s_c[pi][0] - s_c[i][0], dpy = s_c[pi][1] - s_c[i][1];
+            const float sc = sqrtf(dcx * dcx + dcy * dcy) / 2.0f, sp = sqrtf(dpx * dpx + dpy * dpy) / 2.0f;
+            scale = 2.0f * fmaxf(sc, sp);
+        }
+        scale = scale * fmaxf(ratio[i], 0.0f);
+        scale = scale + fmaxf(offset[i], 0.0f);
+        if (i != 0 && vis_thresh > 0.0f) {
+            const float score = bilinear_point(amax + (size_t)b * HW, S, c_part_mask[i], s_c[i][0], s_c[i][1], align_corners);
+            if (score < vis_thresh) scale = 0.8f * scale_box;
+        }
+        float* t = theta + ((size_t)b * 24 + i) * 3;
+        t[0] = scale; t[1] = s_c[i][0]; t[2] = s_c[i][1];
+    }
+}
+
+// 24x affine_grid + grid_sample (iuv_estimator.py:193-204), C % 4 == 0
+__global__ void k_stn_sample(int B, int S, int C, const float* __restrict__ xd, const float* __restrict__ theta,
+                             int align_corners, float* __restrict__ crops) {
+    const int C4 = C >> 2;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)B * 24 * S * S * C4;
+    if (i >= total) return;
+    const int c4 = (int)(i % C4);
+    size_t r = i / C4;
+    const int px = (int)(r % S); r /= S;
+    const int py = (int)(r % S); r /= S;
+    const int part = (int)(r % 24);
+    const int b = (int)(r / 24);
+    const float* t = theta + ((size_t)b * 24 + part) * 3;
+    const float s = t[0], cx = t[1], cy = t[2];
+    float xb, yb;
+    if (align_corners) { xb = -1.0f + 2.0f * (float)px / (float)(S - 1); yb = -1.0f + 2.0f * (float)py / (float)(S - 1); }
+    else { xb = (float)(2 * px + 1) / (float)S - 1.0f; yb = (float)(2 * py + 1) / (float)S - 1.0f; }
+    const float gx = s * xb + cx, gy = s * yb + cy;
+    float ix, iy;
+    if (align_corners) { ix = (gx + 1.0f) * 0.5f * (float)(S - 1); iy = (gy + 1.0f) * 0.5f * (float)(S - 1); }
+    else { ix = ((gx + 1.0f) * (float)S - 1.0f) * 0.5f; iy = ((gy + 1.0f) * (float)S - 1.0f) * 0.5f; }
+    const float fx = floorf(ix), fy = floorf(iy);
+    const float tx = ix - fx, ty = iy - fy;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    // guard against huge coordinates before the int conversion
+    if (fx > -2.0f && fx < (float)S + 1.0f && fy > -2.0f && fy < (float)S + 1.0f) {
+        const int x0 = (int)fx, y0 = (int)fy;
+        const float* base = xd + (size_t)b * S * S * C + (size_t)c4 * 4;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                const int xx = x0 + dx, yy = y0 + dy;
+                if (xx < 0 || xx >= S || yy < 0 || yy >= S) continue;
+                const float w = (dx ? tx : 1.0f - tx) * (dy ? ty : 1.0f - ty);
+                const float4 v = __ldg(reinterpret_cast<const float4*>(base + ((size_t)yy * S + xx) * C));
+                acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
+                acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+            }
+    }
+    reinterpret_cast<float4*>(crops)[i] = acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// HRNet fuse (hr_module.py:161-179): y = relu(sum_j nearest_up(t_j))
+// ------------------------------------------------------------------------------------------
+struct FuseArgs { const float* t[4]; int f[4]; int n; };
+
+__global__ void k_fuse_sum(int N, int H, int W, int C4, FuseArgs a, int relu, float* __restrict__ y) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)N * H * W * C4;
+    if (i >= total) return;
+    const int c4 = (int)(i % C4);
+    size_t r = i / C4;
+    const int w = (int)(r % W); r /= W;
+    const int h = (int)(r % H);
+    const int n = (int)(r / H);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < a.n; ++j) {
+        const int f = a.f[j];
+        const int hh = H / f, ww = W / f;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(a.t[j]) +
+                               (((size_t)n * hh + h / f) * ww + w / f) * C4 + c4);
+        if (j == 0) acc = v;
+        else { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+    }
+    if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+    reinterpret_cast<float4*>(y)[i] = acc;
+}
+
+__global__ void k_maxpool3x3s2(int N, int H, int W, int C4, const float* __restrict__ x, float* __restrict__ y) {
+    const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)N * Ho * Wo * C4;
+    if (i >= total) return;
+    const int c4 = (int)(i % C4);
+    size_t r = i / C4;
+    const int wo = (int)(r % Wo); r /= Wo;
+    const int ho = (int)(r % Ho);
+    const int n = (int)(r / Ho);
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int dy = 0; dy < 3; ++dy) {
+        const int hh = ho * 2 - 1 + dy;
+        if (hh < 0 || hh >= H) continue;
+        for (int dx = 0; dx < 3; ++dx) {
+            const int ww = wo * 2 - 1 + dx;
+            if (ww < 0 || ww >= W) continue;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(x) + (((size_t)n * H + hh) * W + ww) * C4 + c4);
+            m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+        }
+    }
+    reinterpret_cast<float4*>(y)[i] = m;
+}
+
+__global__ void k_global_avgpool(int N, int HW, int C, const float* __restrict__ x, float* __restrict__ y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * C) return;
+    const int n = i / C, c = i % C;
+    float s = 0.f;
+    for (int p = 0; p < HW; ++p) s += x[((size_t)n * HW + p) * C + c];
+    y[i] = s / (float)HW;
+}
+
+__global__ void k_linear(int N, int In, int Out, const float* __restrict__ x, const float* __restrict__ w,
+                         const float* __restrict__ b, const float* __restrict__ add, float* __restrict__ y) {
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (gw >= N * Out) return;
+    const int n = gw / Out, o = gw % Out;
+    float s = 0.f;
+    for (int i = lane; i < In; i += 32) s = fmaf(x[(size_t)n * In + i], w[(size_t)o * In + i], s);
+    s = warp_sum(s);
+    if (lane == 0) y[gw] = s + (b ? b[o] : 0.f) + (add ? add[o] : 0.f);
+}
+
+// ------------------------------------------------------------------------------------------
+// GCN refinement + pose head + rot6d (smpl_regressor.py:858-895,924; GCN.py:29-92)
+// One CTA (256 threads) per sample; thread o owns output column o of each GraphConv.
+// ------------------------------------------------------------------------------------------
+constexpr int kGcnThreads = 256;
+constexpr int kGcnMaxF = 256;
+
+struct GcnArgs {
+    const float* adj;
+    const float* W[5]; const float* b[5]; const float* bn_s[5]; const float* bn_t[5];
+    int din[5], dout[5];
+    const float* head_w; const float* head_b; const float* mean_pose;
+};
+
+__device__ __forceinline__ void rot6d_cols(const float* x, float* R) {
+    const float a1x = x[0], a1y = x[2], a1z = x[4], a2x = x[1], a2y = x[3], a2z = x[5];
+    const float n1 = fmaxf(sqrtf(a1x * a1x + a1y * a1y + a1z * a1z), 1e-12f);
+    const float b1x = a1x / n1, b1y = a1y / n1, b1z = a1z / n1;
+    const float d = b1x * a2x + b1y * a2y + b1z * a2z;
+    const float ux = a2x - d * b1x, uy = a2y - d * b1y, uz = a2z - d * b1z;
+    const float n2 = fmaxf(sqrtf(ux * ux + uy * uy + uz * uz), 1e-12f);
+    const float b2x = ux / n2, b2y = uy / n2, b2z = uz / n2;
+    R[0] = b1x; R[1] = b2x; R[2] = b1y * b2z - b1z * b2y;
+    R[3] = b1y; R[4] = b2y; R[5] = b1z * b2x - b1x * b2z;
+    R[6] = b1z; R[7] = b2z; R[8] = b1x * b2y - b1y * b2x;
+}
+
+__global__ void __launch_bounds__(kGcnThreads)
+k_gcn_pose_head(int B, GcnArgs g, const float* __restrict__ rot_feats, const float* __restrict__ global_para,
+                float* __restrict__ para) {
+    extern __shared__ __align__(16) float s_gcn[];
+    float* s_x = s_gcn;                          // [24][kGcnMaxF] layer input
+    float* s_ax = s_gcn + 24 * kGcnMaxF;         // [24][kGcnMaxF] adj @ x
+    float* s_res = s_gcn + 2 * 24 * kGcnMaxF;    // [24][128] residual (pos_feats_init)
+    float* s_adj = s_res + 24 * 128;             // [24][24]
+    float* s_p6 = s_adj + 576;                   // [144]
+    const int b = blockIdx.x, tid = threadIdx.x;
+    for (int i = tid; i < 24 * 128; i += kGcnThreads) s_x[(i / 128) * kGcnMaxF + (i % 128)] = rot_feats[(size_t)b * 24 * 128 + i];
+    __syncthreads();
+    for (int l = 0; l < 5; ++l) {
+        const int F = g.din[l], Fo = g.dout[l];
+        const int a_id = (l == 0) ? 0 : (l == 4 ? 2 : 1);
+        for (int i = tid; i < 576; i += kGcnThreads) s_adj[i] = g.adj[a_id * 576 + i];
+        __syncthreads();
+        // ax = adj @ x
+        for (int i = tid; i < 24 * F; i += kGcnThreads) {
+            const int n = i / F, f = i % F;
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < 24; ++k) s = fmaf(s_adj[n * 24 + k], s_x[k * kGcnMaxF + f], s);
+            s_ax[n * kGcnMaxF + f] = s;
+        }
+        __syncthreads();
+        // y = relu(bn(ax @ W + b)); thread tid owns column o = tid
+        if (tid < Fo) {
+            float acc[24];
+#pragma unroll
+            for (int n = 0; n < 24; ++n) acc[n] = 0.f;
+            const float* W = g.W[l];
+            for (int f = 0; f < F; ++f) {
+                const float w = __ldg(W + (size_t)f * Fo + tid);
+#pragma unroll
+                for (int n = 0; n < 24; ++n) acc[n] = fmaf(s_ax[n * kGcnMaxF + f], w, acc[n]);
+            }
+            const float bias = g.b[l][tid];
+#pragma unroll
+            for (int n = 0; n < 24; ++n) {
+                float v = (acc[n] + bias) * g.bn_s[l][n] + g.bn_t[l][n];
+                v = fmaxf(v, 0.f);
+                if (l == 3) v += s_res[n * 128 + tid];          // l_pos_feat = pos_feats_init + refine (smpl_regressor.py:873)
+                s_x[n * kGcnMaxF + tid] = v;
+                if (l == 0) s_res[n * 128 + tid] = v;           // pos_feats_init
+            }
+        }
+        __syncthreads();
+    }
+    // pose head: grouped 1x1 conv (24 groups, 128 -> 6) + mean_pose
+    if (tid < 144) {
+        const int j = tid / 6, k = tid % 6;
+        const float* w = g.head_w + ((size_t)j * 6 + k) * 128;
+        float s = 0.f;
+        for (int f = 0; f < 128; ++f) s = fmaf(s_x[j * kGcnMaxF + f], __ldg(w + f), s);
+        s_p6[tid] = s + g.head_b[tid] + g.mean_pose[tid];
+    }
+    __syncthreads();
+    float* out = para + (size_t)b * 229;
+    if (tid < 13) out[tid] = global_para[(size_t)b * 13 + tid];
+    if (tid < 24) {
+        float R[9];
+        rot6d_cols(s_p6 + tid * 6, R);
+#pragma unroll
+        for (int e = 0; e < 9; ++e) out[13 + tid * 9 + e] = R[e];
+    }
+}
+
+}  // namespace danet
+
+using namespace danet;
+
+extern "C" int danet_nchw_to_nhwc(int32_t N, int32_t C, int32_t HW, int32_t Cp, const float* x, float* y,
+                                  danet_stream_t s) {
+    DANET_CHECK(N >= 0 && C > 0 && Cp >= C && HW > 0, "danet_nchw_to_nhwc: bad sizes");
+    if (N == 0) return 0;
+    DANET_CHECK(x && y, "danet_nchw_to_nhwc: null pointer");
+    k_nchw_to_nhwc<<<cdiv(N * HW, 256), 256, 0, (cudaStream_t)s>>>(N, C, HW, Cp, x, y);
+    DANET_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int danet_iuv_clean_global(int32_t B, int32_t HW, int32_t Chead, int32_t off_u, int32_t off_v,
+                                      int32_t off_i, int32_t off_a, int32_t Cbody, const float* heads,
+                                      float* body_iuv, uint8_t* index_argmax, float* u_nchw, float* v_nchw,
+                                      float* i_nchw, float* ann_nchw, danet_stream_t s) {
+    DANET_CHECK(B >= 0 && HW > 0 && Cbody >= 75, "danet_iuv_clean_global: bad sizes");
+    DANET_CHECK(off_u + 25 <= Chead && off_v + 25 <= Chead && off_i + 25 <= Chead && off_a + 15 <= Chead,
+                "danet_iuv_clean_global: head offsets exceed Chead=%d", Chead);
+    if (B == 0) return 0;
+    DANET_CHECK(heads && body_iuv && index_argmax, "danet_iuv_clean_global: null pointer");
+    k_iuv_clean_global<<<cdiv(B * HW, 128), 128, 0, (cudaStream_t)s>>>(B, HW, Chead, off_u, off_v, off_i, off_a, Cbody,
+                                                                     heads, body_iuv, index_argmax, u_nchw, v_nchw,
+                                                                     i_nchw, ann_nchw);
+    DANET_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int danet_iuv_clean_parts(int32_t N, int32_t HW, int32_t Cx, int32_t Cy, const float* x, float* y,
+                                     float* raw_nchw, danet_stream_t s) {
+    DANET_CHECK(N >= 0 && HW > 0 && Cx >= 21 && Cy >= 21, "danet_iuv_clean_parts: bad sizes");
+    if (N == 0) return 0;
+    DANET_CHECK(x && y, "danet_iuv_clean_parts: null pointer");
+    k_iuv_clean_parts<<<cdiv((int64_t)N * HW, 128), 128, 0, (cudaStream_t)s>>>(N, HW, Cx, Cy, x, y, raw_nchw);
+    DANET_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int danet_stn_params(int32_t B, int32_t S, int32_t Chm, const float* hm, const uint8_t* index_argmax,
+                                const float* learned_ratio, const float* learned_offset, float vis_thresh,
+                                int32_t align_corners, float* centers, float* theta, danet_stream_t s) {
+    DANET_CHECK(B >= 0 && S > 1 && Chm >= 24 && Chm % 4 == 0, "danet_stn_params: bad sizes (Chm must be >=24 and %%4==0)");
+    if (B == 0) return 0;
+    DANET_CHECK(hm && index_argmax && learned_ratio && learned_offset && centers && theta, "danet_stn_params: null pointer");
+    k_stn_params<<<B, kStnThreads, 0, (cudaStream_t)s>>>(B, S, Chm, hm, index_argmax, learned_ratio, learned_offset,
+                                                        vis_thresh, align_corners, centers, theta);
+    DANET_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int danet_stn_sample(int32_t B, int32_t S, int32_t C, const float* xd, const float* theta,
+                                int32_t align_corners, float* crops, danet_stream_t s) {
+    DANET_CHECK(B >= 0 && S > 1 && C > 0 && C % 4 == 0, "danet_stn_sample: bad sizes (C %% 4 must be 0)");
+    if (B == 0) return 0;
+    DANET_CHECK(xd && theta && crops, "danet_stn_sample: null pointer");
+    const int64_t total = (int64_t)B * 24 * S * S * (C / 4);
+    k_stn_sample<<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)s>>>(B, S, C, xd, theta, align_corners, crops);
+    DANET_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int danet_fuse_sum(int32_t N, int32_t H, int32_t W, int32_t C, int32_t nterms, const float* const* terms,
+                              const int32_t* factors, int32_t relu, float* y, danet_stream_t s) {
+    DANET_CHECK(N >= 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "danet_fuse_sum: bad sizes (C %% 4 must be 0)");
+    DANET_CHECK(nterms >= 1 && nterms <= 4 && terms && factors && y, "danet_fuse_sum: 1..4 terms required");
+    if (N == 0) return 0;
+    FuseArgs a;
+    a.n = nterms;
+    for (int j = 0; j < 4; ++j) { a.t[j] = nullptr; a.f[j] = 1; }
+    for (int j = 0; j < nterms; ++j) {
+        const int f = factors[j];
+        DANET_CHECK(terms[j] && (f == 1 || f == 2 || f == 4 || f == 8) && H % f == 0 && W % f == 0,
+                    "danet_fuse_sum: term %d has bad upsample factor %d for %dx%d", j, f, H, W);
+        a.t[j] = terms[j]; a.f[j] = f;
+    }
+    const int64_t total = (int64_t)N * H * W * (C / 4);
+    k_fuse_sum<<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)s>>>(N, H, W, C / 4, a, relu, y);
+    DANET_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int danet_maxpool3x3s2(int32_t N, int32_t H, int32_t W, int32_t C, const float* x, float* y, danet_stream_t s) {
+    DANET_CHECK(N >= 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "danet_maxpool3x3s2: bad sizes (C %% 4 must be 0)");
+    if (N == 0) return 0;
+    DANET_CHECK(x && y, "danet_maxpool3x3s2: null pointer");
+    const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    const int64_t total = (int64_t)N * Ho * Wo * (C / 4);
+    k_maxpool3x3s2<<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)s>>>(N, H, W, C / 4, x, y);
+    DANET_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int danet_global_avgpool(int32_t N, int32_t HW, int32_t C, const float* x, float* y, danet_stream_t s) {
+    DANET_CHECK(N >= 0 && HW > 0 && C > 0, "danet_global_avgpool: bad sizes");
+    if (N == 0) return 0;
+    DANET_CHECK(x && y, "danet_global_avgpool: null pointer");
+    k_global_avgpool<<<cdiv(N * C, 256), 256, 0, (cudaStream_t)s>>>(N, HW, C, x, y);
+    DANET_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int danet_linear(int32_t N, int32_t In, int32_t Out, const float* x, const float* w, const float* b,
+                            const float* add, float* y, danet_stream_t s) {
+    DANET_CHECK(N >= 0 && In > 0 && Out > 0, "danet_linear: bad sizes");
+    if (N == 0) return 0;
+    DANET_CHECK(x && w && y, "danet_linear: null pointer");
+    k_linear<<<cdiv(N * Out * 32, 256), 256, 0, (cudaStream_t)s>>>(N, In, Out, x, w, b, add, y);
+    DANET_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int danet_gcn_pose_head(int32_t B, const danet_gcn_params* p, const float* rot_feats,
+                                   const float* global_para, float* para, danet_stream_t s) {
+    DANET_CHECK(B >= 0 && p, "danet_gcn_pose_head: bad arguments");
+    if (B == 0) return 0;
+    DANET_CHECK(rot_feats && global_para && para && p->adj && p->head_w && p->head_b && p->mean_pose,
+                "danet_gcn_pose_head: null pointer");
+    GcnArgs g;
+    g.adj = p->adj; g.head_w = p->head_w; g.head_b = p->head_b; g.mean_pose = p->mean_pose;
+    for (int l = 0; l < 5; ++l) {
+        DANET_CHECK(p->W[l] && p->b[l] && p->bn_scale[l] && p->bn_shift[l], "danet_gcn_pose_head: layer %d has null params", l);
+        DANET_CHECK(p->dim_in[l] > 0 && p->dim_in[l] <= kGcnMaxF && p->dim_out[l] > 0 && p->dim_out[l] <= kGcnMaxF,
+                    "danet_gcn_pose_head: layer %d dims %d->%d exceed %d", l, p->dim_in[l], p->dim_out[l], kGcnMaxF);
+        g.W[l] = p->W[l]; g.b[l] = p->b[l]; g.bn_s[l] = p->bn_scale[l]; g.bn_t[l] = p->bn_shift[l];
+        g.din[l] = p->dim_in[l]; g.dout[l] = p->dim_out[l];
+    }
+    DANET_CHECK(g.din[0] == 128 && g.dout[0] == 128 && g.dout[3] == 128 && g.din[4] == 128 && g.dout[4] == 128,
+                "danet_gcn_pose_head: expected 128-d r2p / refine-out / p2r features");
+    const size_t smem = (size_t)(2 * 24 * kGcnMaxF + 24 * 128 + 576 + 144) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        DANET_CUDA(cudaFuncSetAttribute(k_gcn_pose_head, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    k_gcn_pose_head<<<B, kGcnThreads, smem, (cudaStream_t)s>>>(B, g, rot_feats, global_para, para);
+    DANET_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// iuvmap_clean with the reference's own signature / layout (utils/iuvmap.py:6-38): NCHW maps
+// ------------------------------------------------------------------------------------------
+namespace danet {
+__global__ void k_iuv_clean_nchw(int B, int C, int Ca, int HW, const float* __restrict__ U, const float* __restrict__ V,
+                                 const float* __restrict__ I, const float* __restrict__ A, float* __restrict__ oU,
+                                 float* __restrict__ oV, float* __restrict__ oI, float* __restrict__ oA) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * HW) return;
+    const int b = i / HW, pix = i % HW;
+    int best = 0; float bv = I[((size_t)b * C) * HW + pix];
+    for (int c = 1; c < C; ++c) {
+        const float x = I[((size_t)b * C + c) * HW + pix];
+        if ((x > bv) || (x != x && bv == bv)) { bv = x; best = c; }
+    }
+    for (int c = 0; c < C; ++c) {
+        const size_t o = ((size_t)b * C + c) * HW + pix;
+        const float oh = (c == best) ? 1.0f : 0.0f;
+        oI[o] = oh; oU[o] = oh * U[o]; oV[o] = oh * V[o];
+    }
+    if (A && oA) {
+        int ba = 0; float av = A[((size_t)b * Ca) * HW + pix];
+        for (int c = 1; c < Ca; ++c) {
+            const float x = A[((size_t)b * Ca + c) * HW + pix];
+            if ((x > av) || (x != x && av == av)) { av = x; ba = c; }
+        }
+        for (int c = 0; c < Ca; ++c) oA[((size_t)b * Ca + c) * HW + pix] = (c == ba) ? 1.0f : 0.0f;
+    }
+}
+}  // namespace danet
+
+extern "C" int danet_iuvmap_clean_nchw(int32_t B, int32_t C, int32_t Ca, int32_t HW, const float* U, const float* V,
+                                       const float* I, const float* A, float* oU, float* oV, float* oI, float* oA,
+                                       danet_stream_t s) {
+    DANET_CHECK(B >= 0 && C > 0 && HW > 0, "danet_iuvmap_clean_nchw: bad sizes");
+    if (B == 0) return 0;
+    DANET_CHECK(U && V && I && oU && oV && oI, "danet_iuvmap_clean_nchw: null pointer");
+    danet::k_iuv_clean_nchw<<<danet::cdiv(B * HW, 256), 256, 0, (cudaStream_t)s>>>(B, C, Ca, HW, U, V, I, A, oU, oV, oI, oA);
+    DANET_LAUNCH_CHECK();
+    return 0;
+}

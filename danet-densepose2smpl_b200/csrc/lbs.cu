@@ -1,0 +1,658 @@
+// Fused SMPL layer for sm_100a: pose front-ends (rot-mat / axis-angle / rot6d), 24-joint
+// kinematic chain, blend shapes + pose correctives + linear blend skinning for 6890 vertices,
+// and the vertex-regressed joints (extra 9, H36M 17, 21 picked vertices) -> 49-joint output.
+//
+// Replaces models/smpl.py:15-46 + smplx.lbs (third-party, see oracle/lbs.py) and
+// utils/geometry.py:9-91.  fp32 SIMT: the products are 3x3 / 3x4 / 207-long dot products per
+// vertex coordinate -- no tensor-core shape.  Three launches per forward:
+//   k_smpl_pose    one thread per body: rotations, rest joints (linear in beta, precomputed
+//                  J_template + J_shapedirs*beta), chain -> A[B,24,3x4], pose_feature[B,208]
+//   k_smpl_verts   grid (54 vertex tiles, B/NB body chunks), 128 threads:
+//                    phase 1 (coordinate-parallel, coalesced 4-byte lanes): v_posed for NB bodies,
+//                            posedirs/shapedirs rows reused from registers across the NB bodies
+//                    phase 2 (vertex-parallel): skinning from smem-resident A, result staged in smem
+//                    phase 3: coalesced store + per-tile partial sums of the sparse joint regressors
+//   k_smpl_joints  one CTA per body: reduce partials in fixed tile order (deterministic), pick
+//                  vertices, apply joint_map.
+#include "common.cuh"
+
+namespace danet {
+
+constexpr int kJ = 24;
+constexpr int kTileV = 128;             // vertices per CTA tile
+constexpr int kTileC = kTileV * 3;      // coordinates per CTA tile
+constexpr int kPF = 208;                // padded pose-feature length (207 -> 208)
+constexpr int kMaxBetas = 16;
+
+struct SmplView {
+    int nv, ntiles, nvpad, npad, nbetas;
+    const float* vt;          // [npad]
+    const float* sd;          // [nbetas][npad]
+    const float* pd;          // [kPF][npad]
+    const float* Jt;          // [72]
+    const float* Jsd;         // [72][nbetas]
+    int parents[kJ];
+    int skin_packed;          // 1: <=4 influences per vertex
+    const uint32_t* skin_idx; // [nvpad] 4 x u8
+    const float4* skin_w;     // [nvpad]
+    const float* skin_dense;  // [24][nvpad]
+    const float* reg_rows;    // [nrows][nvpad]
+    int nrows, npairs;
+    const int* tile_pair_off; // [ntiles+1]
+    const int* tile_pair_row; // [npairs]
+    const int* row_pair_off;  // [nrows+1]
+    const int* row_pair_slot; // [npairs]
+    int nsel; const int* sel; // picked vertices
+    int nextra, nh36m;
+    int nout; const int* joint_map;
+};
+
+}  // namespace danet
+
+struct danet_smpl {
+    danet::SmplView v;
+    std::vector<void*> allocs;
+};
+
+namespace danet {
+
+// ---------------------------------------------------------------------------------------------
+// rotation front-ends
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void rodrigues_smplx(const float* v, float* R) {
+    // smplx.lbs.batch_rodrigues: angle = |v + 1e-8|, d = v / angle, R = I + sin K + (1-cos) K K
+    const float ax = v[0] + 1e-8f, ay = v[1] + 1e-8f, az = v[2] + 1e-8f;
+    const float angle = sqrtf(ax * ax + ay * ay + az * az);
+    const float x = v[0] / angle, y = v[1] / angle, z = v[2] / angle;
+    const float s = sinf(angle), c1 = 1.0f - cosf(angle);
+    R[0] = 1.0f + c1 * (-(z * z) - y * y); R[1] = s * (-z) + c1 * (x * y);      R[2] = s * y + c1 * (x * z);
+    R[3] = s * z + c1 * (x * y);           R[4] = 1.0f + c1 * (-(z * z) - x * x); R[5] = s * (-x) + c1 * (y * z);
+    R[6] = s * (-y) + c1 * (x * z);        R[7] = s * x + c1 * (y * z);          R[8] = 1.0f + c1 * (-(y * y) - x * x);
+}
+
+__device__ __forceinline__ void rodrigues_quat(const float* v, float* R) {
+    // utils/geometry.py:9-45
+    const float ax = v[0] + 1e-8f, ay = v[1] + 1e-8f, az = v[2] + 1e-8f;
+    const float l = sqrtf(ax * ax + ay * ay + az * az);
+    const float nx = v[0] / l, ny = v[1] / l, nz = v[2] / l;
+    const float h = l * 0.5f;
+    const float sn = sinf(h);
+    float w = cosf(h), x = sn * nx, y = sn * ny, z = sn * nz;
+    const float qn = sqrtf(w * w + x * x + y * y + z * z);
+    w /= qn; x /= qn; y /= qn; z /= qn;
+    const float w2 = w * w, x2 = x * x, y2 = y * y, z2 = z * z;
+    const float wx = w * x, wy = w * y, wz = w * z, xy = x * y, xz = x * z, yz = y * z;
+    R[0] = w2 + x2 - y2 - z2; R[1] = 2 * xy - 2 * wz;   R[2] = 2 * wy + 2 * xz;
+    R[3] = 2 * wz + 2 * xy;   R[4] = w2 - x2 + y2 - z2; R[5] = 2 * yz - 2 * wx;
+    R[6] = 2 * xz - 2 * wy;   R[7] = 2 * wx + 2 * yz;   R[8] = w2 - x2 - y2 + z2;
+}
+
+__device__ __forceinline__ void rot6d(const float* x, float* R) {
+    // utils/geometry.py:47-61: x viewed [3,2]; a1 = x[:,0], a2 = x[:,1]; columns (b1,b2,b3)
+    const float a1x = x[0], a1y = x[2], a1z = x[4];
+    const float a2x = x[1], a2y = x[3], a2z = x[5];
+    const float n1 = fmaxf(sqrtf(a1x * a1x + a1y * a1y + a1z * a1z), 1e-12f);
+    const float b1x = a1x / n1, b1y = a1y / n1, b1z = a1z / n1;
+    const float d = b1x * a2x + b1y * a2y + b1z * a2z;
+    const float ux = a2x - d * b1x, uy = a2y - d * b1y, uz = a2z - d * b1z;
+    const float n2 = fmaxf(sqrtf(ux * ux + uy * uy + uz * uz), 1e-12f);
+    const float b2x = ux / n2, b2y = uy / n2, b2z = uz / n2;
+    const float b3x = b1y * b2z - b1z * b2y;
+    const float b3y = b1z * b2x - b1x * b2z;
+    const float b3z = b1x * b2y - b1y * b2x;
+    R[0] = b1x; R[1] = b2x; R[2] = b3x;
+    R[3] = b1y; R[4] = b2y; R[5] = b3y;
+    R[6] = b1z; R[7] = b2z; R[8] = b3z;
+}
+
+__global__ void k_rot6d(int n, const float* __restrict__ x, float* __restrict__ R) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float in[6], out[9];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) in[k] = x[(size_t)i * 6 + k];
+    rot6d(in, out);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) R[(size_t)i * 9 + k] = out[k];
+}
+
+__global__ void k_rodrigues(int n, const float* __restrict__ aa, float* __restrict__ R, int flavor) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float in[3] = {aa[(size_t)i * 3], aa[(size_t)i * 3 + 1], aa[(size_t)i * 3 + 2]}, out[9];
+    if (flavor == 1) rodrigues_smplx(in, out); else rodrigues_quat(in, out);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) R[(size_t)i * 9 + k] = out[k];
+}
+
+__global__ void k_persp(int B, int N, const float* __restrict__ pts, const float* __restrict__ rot,
+                        const float* __restrict__ tr, const float* __restrict__ focal,
+                        const float* __restrict__ center, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * N) return;
+    const int b = i / N;
+    const float* R = rot + (size_t)b * 9;
+    const float px = pts[(size_t)i * 3], py = pts[(size_t)i * 3 + 1], pz = pts[(size_t)i * 3 + 2];
+    const float x = R[0] * px + R[1] * py + R[2] * pz + tr[b * 3 + 0];
+    const float y = R[3] * px + R[4] * py + R[5] * pz + tr[b * 3 + 1];
+    const float z = R[6] * px + R[7] * py + R[8] * pz + tr[b * 3 + 2];
+    const float xn = x / z, yn = y / z, zn = z / z;
+    out[(size_t)i * 2 + 0] = focal[b] * xn + center[b * 2 + 0] * zn;
+    out[(size_t)i * 2 + 1] = focal[b] * yn + center[b * 2 + 1] * zn;
+}
+
+__global__ void k_mpjpe(int B, const float* __restrict__ j17, const float* __restrict__ gt14,
+                        float* __restrict__ out) {
+    // eval.py:202-212 with constants.H36M_TO_J14 (constants.py:95-96)
+    const int sel[14] = {6, 5, 4, 1, 2, 3, 16, 15, 14, 11, 12, 13, 8, 10};
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const float* p = j17 + (size_t)b * 51;
+    float acc = 0.0f;
+    for (int j = 0; j < 14; ++j) {
+        float s = 0.0f;
+        for (int c = 0; c < 3; ++c) {
+            const float d = (p[sel[j] * 3 + c] - p[c]) - gt14[((size_t)b * 14 + j) * 3 + c];
+            s += d * d;
+        }
+        acc += sqrtf(s);
+    }
+    out[b] = acc / 14.0f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_smpl_pose
+// ---------------------------------------------------------------------------------------------
+__global__ void k_smpl_pose(int B, int pose_kind, const float* __restrict__ betas,
+                            const float* __restrict__ pose, SmplView m, float* __restrict__ rot_out,
+                            float* __restrict__ G, float* __restrict__ A, float* __restrict__ pf,
+                            float* __restrict__ posed) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float beta[kMaxBetas];
+    for (int l = 0; l < m.nbetas; ++l) beta[l] = betas[(size_t)b * m.nbetas + l];
+    float J[kJ * 3];
+    for (int e = 0; e < kJ * 3; ++e) {
+        float v = m.Jt[e];
+        for (int l = 0; l < m.nbetas; ++l) v = fmaf(beta[l], m.Jsd[e * m.nbetas + l], v);
+        J[e] = v;
+    }
+    float* Gb = G + (size_t)b * kJ * 12;
+    float* Ab = A + (size_t)b * kJ * 12;
+    float* pfb = pf + (size_t)b * kPF;
+    for (int i = 0; i < kJ; ++i) {
+        float R[9];
+        if (pose_kind == DANET_POSE_ROTMAT) {
+            for (int e = 0; e < 9; ++e) R[e] = pose[((size_t)b * kJ + i) * 9 + e];
+        } else if (pose_kind == DANET_POSE_AXIS_ANGLE) {
+            const float v[3] = {pose[((size_t)b * kJ + i) * 3], pose[((size_t)b * kJ + i) * 3 + 1],
+                                pose[((size_t)b * kJ + i) * 3 + 2]};
+            rodrigues_smplx(v, R);
+        } else {
+            float v[6];
+            for (int e = 0; e < 6; ++e) v[e] = pose[((size_t)b * kJ + i) * 6 + e];
+            rot6d(v, R);
+        }
+        if (rot_out) for (int e = 0; e < 9; ++e) rot_out[((size_t)b * kJ + i) * 9 + e] = R[e];
+        if (i > 0) for (int e = 0; e < 9; ++e) pfb[(i - 1) * 9 + e] = R[e] - ((e % 4 == 0) ? 1.0f : 0.0f);
+        float g[12];
+        if (i == 0) {
+            for (int r = 0; r < 3; ++r) {
+                g[r * 4 + 0] = R[r * 3 + 0]; g[r * 4 + 1] = R[r * 3 + 1]; g[r * 4 + 2] = R[r * 3 + 2];
+                g[r * 4 + 3] = J[r];
+            }
+        } else {
+            const int p = m.parents[i];
+            const float* gp = Gb + p * 12;
+            const float rel[3] = {J[i * 3] - J[p * 3], J[i * 3 + 1] - J[p * 3 + 1], J[i * 3 + 2] - J[p * 3 + 2]};
+            for (int r = 0; r < 3; ++r) {
+                const float a0 = gp[r * 4], a1 = gp[r * 4 + 1], a2 = gp[r * 4 + 2], a3 = gp[r * 4 + 3];
+                g[r * 4 + 0] = a0 * R[0] + a1 * R[3] + a2 * R[6];
+                g[r * 4 + 1] = a0 * R[1] + a1 * R[4] + a2 * R[7];
+                g[r * 4 + 2] = a0 * R[2] + a1 * R[5] + a2 * R[8];
+                g[r * 4 + 3] = a0 * rel[0] + a1 * rel[1] + a2 * rel[2] + a3;
+            }
+        }
+        for (int e = 0; e < 12; ++e) Gb[i * 12 + e] = g[e];
+        for (int r = 0; r < 3; ++r) {
+            posed[((size_t)b * kJ + i) * 3 + r] = g[r * 4 + 3];
+            Ab[i * 12 + r * 4 + 0] = g[r * 4 + 0];
+            Ab[i * 12 + r * 4 + 1] = g[r * 4 + 1];
+            Ab[i * 12 + r * 4 + 2] = g[r * 4 + 2];
+            Ab[i * 12 + r * 4 + 3] = g[r * 4 + 3] -
+                (g[r * 4 + 0] * J[i * 3] + g[r * 4 + 1] * J[i * 3 + 1] + g[r * 4 + 2] * J[i * 3 + 2]);
+        }
+    }
+    pfb[207] = 0.0f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_smpl_verts
+// ---------------------------------------------------------------------------------------------
+template <int NB>
+__global__ void __launch_bounds__(kTileV)
+k_smpl_verts(int B, const float* __restrict__ betas, const float* __restrict__ pf,
+             const float* __restrict__ A, SmplView m, float* __restrict__ verts,
+             float* __restrict__ partials) {
+    extern __shared__ __align__(16) float smem_lbs[];
+    float (*s_pf)[kPF] = reinterpret_cast<float (*)[kPF]>(smem_lbs);
+    float (*s_A)[kJ * 12] = reinterpret_cast<float (*)[kJ * 12]>(smem_lbs + NB * kPF);
+    float (*s_v)[kTileC] = reinterpret_cast<float (*)[kTileC]>(smem_lbs + NB * (kPF + kJ * 12));
+    float (*s_beta)[kMaxBetas] = reinterpret_cast<float (*)[kMaxBetas]>(smem_lbs + NB * (kPF + kJ * 12 + kTileC));
+
+    const int tile = blockIdx.x, b0 = blockIdx.y * NB, tid = threadIdx.x;
+    for (int i = tid; i < NB * kPF; i += kTileV) {
+        const int b = i / kPF, k = i % kPF, bb = min(b0 + b, B - 1);
+        s_pf[b][k] = pf[(size_t)bb * kPF + k];
+    }
+    for (int i = tid; i < NB * kJ * 12; i += kTileV) {
+        const int b = i / (kJ * 12), k = i % (kJ * 12), bb = min(b0 + b, B - 1);
+        s_A[b][k] = A[(size_t)bb * kJ * 12 + k];
+    }
+    for (int i = tid; i < NB * kMaxBetas; i += kTileV) {
+        const int b = i / kMaxBetas, l = i % kMaxBetas, bb = min(b0 + b, B - 1);
+        s_beta[b][l] = l < m.nbetas ? betas[(size_t)bb * m.nbetas + l] : 0.0f;
+    }
+    __syncthreads();
+
+    // ---- phase 1: v_posed[n] for n = tile*384 + tid + {0,128,256}, NB bodies ----
+    const size_t n0 = (size_t)tile * kTileC + tid;
+    float acc[3][NB];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const float t = __ldg(m.vt + n0 + j * kTileV);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) acc[j][b] = t;
+    }
+    for (int l = 0; l < m.nbetas; ++l) {
+        float s[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) s[j] = __ldg(m.sd + (size_t)l * m.npad + n0 + j * kTileV);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const float bl = s_beta[b][l];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) acc[j][b] = fmaf(bl, s[j], acc[j][b]);
+        }
+    }
+#pragma unroll 2
+    for (int k = 0; k < kPF; k += 4) {
+        float p[4][3];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) p[kk][j] = __ldg(m.pd + (size_t)(k + kk) * m.npad + n0 + j * kTileV);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const float4 f = *reinterpret_cast<const float4*>(&s_pf[b][k]);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                float a = acc[j][b];
+                a = fmaf(f.x, p[0][j], a);
+                a = fmaf(f.y, p[1][j], a);
+                a = fmaf(f.z, p[2][j], a);
+                a = fmaf(f.w, p[3][j], a);
+                acc[j][b] = a;
+            }
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) s_v[b][tid + j * kTileV] = acc[j][b];
+    __syncthreads();
+
+    // ---- phase 2: skinning, thread = vertex ----
+    const int v = tile * kTileV + tid;
+    if (m.skin_packed) {
+        const uint32_t idx = __ldg(m.skin_idx + v);
+        const float4 w = __ldg(m.skin_w + v);
+        const int j0 = idx & 255, j1 = (idx >> 8) & 255, j2 = (idx >> 16) & 255, j3 = idx >> 24;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const float x = s_v[b][3 * tid], y = s_v[b][3 * tid + 1], z = s_v[b][3 * tid + 2];
+            float o[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                float t[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int e = r * 4 + c;
+                    t[c] = w.x * s_A[b][j0 * 12 + e] + w.y * s_A[b][j1 * 12 + e] +
+                           w.z * s_A[b][j2 * 12 + e] + w.w * s_A[b][j3 * 12 + e];
+                }
+                o[r] = t[0] * x + t[1] * y + t[2] * z + t[3];
+            }
+            s_v[b][3 * tid] = o[0]; s_v[b][3 * tid + 1] = o[1]; s_v[b][3 * tid + 2] = o[2];
+        }
+    } else {
+        float w[kJ];
+#pragma unroll
+        for (int j = 0; j < kJ; ++j) w[j] = __ldg(m.skin_dense + (size_t)j * m.nvpad + v);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const float x = s_v[b][3 * tid], y = s_v[b][3 * tid + 1], z = s_v[b][3 * tid + 2];
+            float o[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                float t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int j = 0; j < kJ; ++j)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) t[c] = fmaf(w[j], s_A[b][j * 12 + r * 4 + c], t[c]);
+                o[r] = t[0] * x + t[1] * y + t[2] * z + t[3];
+            }
+            s_v[b][3 * tid] = o[0]; s_v[b][3 * tid + 1] = o[1]; s_v[b][3 * tid + 2] = o[2];
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 3: coalesced store + joint-regressor partial sums ----
+    const int ncoord = m.nv * 3;
+    if (verts) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            if (b0 + b < B) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const int gn = tile * kTileC + tid + j * kTileV;
+                    if (gn < ncoord) verts[(size_t)(b0 + b) * ncoord + gn] = s_v[b][tid + j * kTileV];
+                }
+            }
+        }
+    }
+    const int warp = tid >> 5, lane = tid & 31;
+    const int off = m.tile_pair_off[tile], npair = m.tile_pair_off[tile + 1] - off;
+    for (int q = warp; q < npair * NB; q += kTileV / 32) {
+        const int pr = q / NB, b = q % NB;
+        const int row = m.tile_pair_row[off + pr];
+        const float* rr = m.reg_rows + (size_t)row * m.nvpad + (size_t)tile * kTileV;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < kTileV / 32; ++i) {
+            const int vv = lane + i * 32;
+            const float r = __ldg(rr + vv);
+            s0 = fmaf(r, s_v[b][3 * vv], s0);
+            s1 = fmaf(r, s_v[b][3 * vv + 1], s1);
+            s2 = fmaf(r, s_v[b][3 * vv + 2], s2);
+        }
+        s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
+        if (lane == 0 && b0 + b < B) {
+            float* dst = partials + ((size_t)(b0 + b) * m.npairs + off + pr) * 3;
+            dst[0] = s0; dst[1] = s1; dst[2] = s2;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_smpl_joints
+// ---------------------------------------------------------------------------------------------
+__global__ void k_smpl_joints(int B, SmplView m, const float* __restrict__ posed,
+                              const float* __restrict__ verts, const float* __restrict__ partials,
+                              float* __restrict__ joints, float* __restrict__ smpl_joints,
+                              float* __restrict__ joints_h36m) {
+    extern __shared__ float s_j[];          // [(24 + nsel + nrows) * 3]
+    const int b = blockIdx.x;
+    const int ncat = kJ + m.nsel + m.nrows;
+    for (int t = threadIdx.x; t < ncat * 3; t += blockDim.x) {
+        const int i = t / 3, c = t % 3;
+        float val;
+        if (i < kJ) {
+            val = posed[((size_t)b * kJ + i) * 3 + c];
+        } else if (i < kJ + m.nsel) {
+            val = verts[((size_t)b * m.nv + m.sel[i - kJ]) * 3 + c];
+        } else {
+            const int row = i - kJ - m.nsel;
+            val = 0.0f;
+            for (int q = m.row_pair_off[row]; q < m.row_pair_off[row + 1]; ++q)
+                val += partials[((size_t)b * m.npairs + m.row_pair_slot[q]) * 3 + c];
+        }
+        s_j[t] = val;
+    }
+    __syncthreads();
+    if (joints)
+        for (int t = threadIdx.x; t < m.nout * 3; t += blockDim.x)
+            joints[(size_t)b * m.nout * 3 + t] = s_j[m.joint_map[t / 3] * 3 + t % 3];
+    if (smpl_joints)
+        for (int t = threadIdx.x; t < kJ * 3; t += blockDim.x) smpl_joints[(size_t)b * kJ * 3 + t] = s_j[t];
+    if (joints_h36m && m.nh36m > 0)
+        for (int t = threadIdx.x; t < m.nh36m * 3; t += blockDim.x)
+            joints_h36m[(size_t)b * m.nh36m * 3 + t] = s_j[(kJ + m.nsel + m.nextra) * 3 + t];
+}
+
+template <typename T>
+static int up(danet_smpl* h, const T** dst, const std::vector<T>& src) {
+    T* d = nullptr;
+    if (upload(&d, src.data(), src.size()) != 0) return -1;
+    h->allocs.push_back(d);
+    *dst = d;
+    return 0;
+}
+
+}  // namespace danet
+
+using namespace danet;
+
+extern "C" int danet_smpl_create(const danet_smpl_desc* d, danet_smpl_t* out) {
+    DANET_CHECK(d && out, "danet_smpl_create: null argument");
+    DANET_CHECK(d->num_joints == kJ, "danet_smpl_create: num_joints must be 24 (got %d)", d->num_joints);
+    DANET_CHECK(d->num_betas >= 1 && d->num_betas <= kMaxBetas, "danet_smpl_create: num_betas %d not in 1..16", d->num_betas);
+    DANET_CHECK(d->num_verts > 0 && d->v_template && d->shapedirs && d->posedirs && d->J_regressor &&
+                d->lbs_weights && d->parents, "danet_smpl_create: missing model array");
+    DANET_CHECK(d->parents[0] < 0, "danet_smpl_create: parents[0] must be -1");
+    for (int i = 1; i < kJ; ++i)
+        DANET_CHECK(d->parents[i] >= 0 && d->parents[i] < i, "danet_smpl_create: parents must precede children");
+    const int nv = d->num_verts, nb = d->num_betas;
+    auto* h = new danet_smpl();
+    SmplView& m = h->v;
+    m.nv = nv; m.ntiles = cdiv(nv, kTileV); m.nvpad = m.ntiles * kTileV; m.npad = m.nvpad * 3; m.nbetas = nb;
+    for (int i = 0; i < kJ; ++i) m.parents[i] = d->parents[i];
+
+    std::vector<float> vt(m.npad, 0.f), sd((size_t)nb * m.npad, 0.f), pd((size_t)kPF * m.npad, 0.f);
+    for (int i = 0; i < nv * 3; ++i) vt[i] = d->v_template[i];
+    for (int i = 0; i < nv * 3; ++i)
+        for (int l = 0; l < nb; ++l) sd[(size_t)l * m.npad + i] = d->shapedirs[(size_t)i * nb + l];
+    for (int k = 0; k < 207; ++k)
+        for (int i = 0; i < nv * 3; ++i) pd[(size_t)k * m.npad + i] = d->posedirs[(size_t)k * nv * 3 + i];
+    // rest joints are linear in beta: J = J_regressor (v_template + S beta)
+    std::vector<float> Jt(kJ * 3), Jsd((size_t)kJ * 3 * nb);
+    for (int j = 0; j < kJ; ++j)
+        for (int c = 0; c < 3; ++c) {
+            double a = 0.0;
+            std::vector<double> s(nb, 0.0);
+            for (int v = 0; v < nv; ++v) {
+                const double r = d->J_regressor[(size_t)j * nv + v];
+                if (r == 0.0) continue;
+                a += r * d->v_template[v * 3 + c];
+                for (int l = 0; l < nb; ++l) s[l] += r * d->shapedirs[((size_t)v * 3 + c) * nb + l];
+            }
+            Jt[j * 3 + c] = (float)a;
+            for (int l = 0; l < nb; ++l) Jsd[(size_t)(j * 3 + c) * nb + l] = (float)s[l];
+        }
+    // skinning weights: packed (<= 4 influences) or dense
+    int maxnnz = 0;
+    for (int v = 0; v < nv; ++v) {
+        int nnz = 0;
+        for (int j = 0; j < kJ; ++j) nnz += d->lbs_weights[(size_t)v * kJ + j] != 0.0f;
+        maxnnz = nnz > maxnnz ? nnz : maxnnz;
+    }
+    m.skin_packed = maxnnz <= 4;
+    m.skin_idx = nullptr; m.skin_w = nullptr; m.skin_dense = nullptr;
+    int rc = 0;
+    if (m.skin_packed) {
+        std::vector<uint32_t> idx(m.nvpad, 0u);
+        std::vector<float4> w(m.nvpad, make_float4(0.f, 0.f, 0.f, 0.f));
+        for (int v = 0; v < nv; ++v) {
+            int k = 0; uint32_t pk = 0; float ww[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int j = 0; j < kJ; ++j) {
+                const float x = d->lbs_weights[(size_t)v * kJ + j];
+                if (x != 0.0f) { pk |= (uint32_t)j << (8 * k); ww[k] = x; ++k; }
+            }
+            idx[v] = pk; w[v] = make_float4(ww[0], ww[1], ww[2], ww[3]);
+        }
+        rc |= up(h, &m.skin_idx, idx); rc |= up(h, &m.skin_w, w);
+    } else {
+        std::vector<float> wd((size_t)kJ * m.nvpad, 0.f);
+        for (int v = 0; v < nv; ++v)
+            for (int j = 0; j < kJ; ++j) wd[(size_t)j * m.nvpad + v] = d->lbs_weights[(size_t)v * kJ + j];
+        rc |= up(h, &m.skin_dense, wd);
+    }
+    // vertex-regressed joints: stacked rows (extra ; h36m), tile-sparse pair lists
+    m.nextra = d->num_extra; m.nh36m = d->J_regressor_h36m ? d->num_h36m : 0;
+    m.nrows = m.nextra + m.nh36m;
+    std::vector<float> rows((size_t)(m.nrows > 0 ? m.nrows : 1) * m.nvpad, 0.f);
+    for (int r = 0; r < m.nextra; ++r)
+        for (int v = 0; v < nv; ++v) rows[(size_t)r * m.nvpad + v] = d->J_regressor_extra[(size_t)r * nv + v];
+    for (int r = 0; r < m.nh36m; ++r)
+        for (int v = 0; v < nv; ++v) rows[(size_t)(m.nextra + r) * m.nvpad + v] = d->J_regressor_h36m[(size_t)r * nv + v];
+    std::vector<int> tpo(m.ntiles + 1, 0), tpr;
+    std::vector<std::vector<int>> row_slots(m.nrows > 0 ? m.nrows : 1);
+    for (int t = 0; t < m.ntiles; ++t) {
+        tpo[t] = (int)tpr.size();
+        for (int r = 0; r < m.nrows; ++r) {
+            bool nz = false;
+            for (int v = t * kTileV; v < (t + 1) * kTileV && !nz; ++v) nz = rows[(size_t)r * m.nvpad + v] != 0.0f;
+            if (nz) { row_slots[r].push_back((int)tpr.size()); tpr.push_back(r); }
+        }
+    }
+    tpo[m.ntiles] = (int)tpr.size();
+    m.npairs = (int)tpr.size();
+    std::vector<int> rpo(m.nrows + 1, 0), rps;
+    for (int r = 0; r < m.nrows; ++r) { rpo[r] = (int)rps.size(); for (int s : row_slots[r]) rps.push_back(s); }
+    rpo[m.nrows] = (int)rps.size();
+    if (tpr.empty()) tpr.push_back(0);
+    if (rps.empty()) rps.push_back(0);
+    m.nsel = d->num_selected;
+    std::vector<int> sel(d->selected_verts, d->selected_verts + d->num_selected);
+    if (sel.empty()) sel.push_back(0);
+    for (int i = 0; i < d->num_selected; ++i)
+        if (sel[i] < 0 || sel[i] >= nv) { set_error("danet_smpl_create: selected vertex %d out of range", sel[i]); delete h; return -1; }
+    m.nout = d->num_out_joints;
+    std::vector<int> jm(d->joint_map, d->joint_map + d->num_out_joints);
+    const int ncat = kJ + m.nsel + m.nextra;
+    for (int i = 0; i < m.nout; ++i)
+        if (jm[i] < 0 || jm[i] >= ncat) { set_error("danet_smpl_create: joint_map[%d]=%d out of range 0..%d", i, jm[i], ncat - 1); delete h; return -1; }
+    if (jm.empty()) jm.push_back(0);
+
+    rc |= up(h, &m.vt, vt); rc |= up(h, &m.sd, sd); rc |= up(h, &m.pd, pd);
+    rc |= up(h, &m.Jt, Jt); rc |= up(h, &m.Jsd, Jsd);
+    rc |= up(h, &m.reg_rows, rows);
+    rc |= up(h, &m.tile_pair_off, tpo); rc |= up(h, &m.tile_pair_row, tpr);
+    rc |= up(h, &m.row_pair_off, rpo); rc |= up(h, &m.row_pair_slot, rps);
+    rc |= up(h, &m.sel, sel); rc |= up(h, &m.joint_map, jm);
+    if (rc != 0) { danet_smpl_destroy(h); return -2; }
+    *out = h;
+    return 0;
+}
+
+extern "C" int danet_smpl_destroy(danet_smpl_t h) {
+    if (!h) return 0;
+    for (void* p : h->allocs) cudaFree(p);
+    delete h;
+    return 0;
+}
+
+static inline int64_t ws_off(int64_t& cur, int64_t bytes) { int64_t o = cur; cur = align_up(cur + bytes, 256); return o; }
+
+extern "C" int64_t danet_smpl_workspace_bytes(danet_smpl_t h, int32_t B) {
+    if (!h || B <= 0) return 0;
+    int64_t cur = 0;
+    ws_off(cur, (int64_t)B * kJ * 12 * 4);          // G
+    ws_off(cur, (int64_t)B * kJ * 12 * 4);          // A
+    ws_off(cur, (int64_t)B * kPF * 4);              // pose feature
+    ws_off(cur, (int64_t)B * kJ * 3 * 4);           // posed joints
+    ws_off(cur, (int64_t)B * (h->v.npairs > 0 ? h->v.npairs : 1) * 3 * 4);  // regressor partials
+    return cur;
+}
+
+extern "C" int danet_smpl_forward(danet_smpl_t h, int32_t B, const float* betas, const float* pose,
+                                  int32_t pose_kind, float* verts, float* joints, float* smpl_joints,
+                                  float* joints_h36m, float* rotmats, void* workspace,
+                                  int32_t bodies_per_cta, danet_stream_t stream_) {
+    DANET_CHECK(h, "danet_smpl_forward: null handle");
+    DANET_CHECK(B > 0, "danet_smpl_forward: empty batch (B=%d)", B);
+    DANET_CHECK(betas && pose && workspace, "danet_smpl_forward: null input/workspace pointer");
+    DANET_CHECK(pose_kind >= 0 && pose_kind <= 2, "danet_smpl_forward: bad pose_kind %d", pose_kind);
+    DANET_CHECK(verts || !(joints || smpl_joints || joints_h36m),
+                "danet_smpl_forward: joint outputs need the verts buffer (picked vertices are read from it)");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const SmplView& m = h->v;
+    char* ws = (char*)workspace;
+    int64_t cur = 0;
+    float* G = (float*)(ws + ws_off(cur, (int64_t)B * kJ * 12 * 4));
+    float* A = (float*)(ws + ws_off(cur, (int64_t)B * kJ * 12 * 4));
+    float* pf = (float*)(ws + ws_off(cur, (int64_t)B * kPF * 4));
+    float* posed = (float*)(ws + ws_off(cur, (int64_t)B * kJ * 3 * 4));
+    float* partials = (float*)(ws + ws_off(cur, (int64_t)B * (m.npairs > 0 ? m.npairs : 1) * 3 * 4));
+
+    k_smpl_pose<<<cdiv(B, 64), 64, 0, stream>>>(B, pose_kind, betas, pose, m, rotmats, G, A, pf, posed);
+    DANET_LAUNCH_CHECK();
+    int nb = bodies_per_cta;
+    if (nb <= 0) nb = B >= 2048 ? 16 : (B >= 32 ? 8 : (B >= 4 ? 4 : (B >= 2 ? 2 : 1)));
+    dim3 grid(m.ntiles, cdiv(B, nb));
+    const size_t smem = (size_t)nb * (kPF + kJ * 12 + kTileC + kMaxBetas) * sizeof(float);
+#define DANET_LBS_LAUNCH(NBV)                                                                       \
+    do {                                                                                            \
+        static bool attr_set = false;                                                               \
+        if (!attr_set) {                                                                            \
+            DANET_CUDA(cudaFuncSetAttribute(k_smpl_verts<NBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                            (int)((size_t)NBV * (kPF + kJ * 12 + kTileC + kMaxBetas) * sizeof(float)))); \
+            attr_set = true;                                                                        \
+        }                                                                                           \
+        k_smpl_verts<NBV><<<grid, kTileV, smem, stream>>>(B, betas, pf, A, m, verts, partials);     \
+    } while (0)
+    switch (nb) {
+        case 1:  DANET_LBS_LAUNCH(1); break;
+        case 2:  DANET_LBS_LAUNCH(2); break;
+        case 4:  DANET_LBS_LAUNCH(4); break;
+        case 8:  DANET_LBS_LAUNCH(8); break;
+        case 16: DANET_LBS_LAUNCH(16); break;
+        default: DANET_CHECK(false, "danet_smpl_forward: bodies_per_cta must be 0,1,2,4,8,16 (got %d)", nb);
+    }
+#undef DANET_LBS_LAUNCH
+    DANET_LAUNCH_CHECK();
+    if (joints || smpl_joints || joints_h36m) {
+        const int ncat = kJ + m.nsel + m.nrows;
+        k_smpl_joints<<<B, 192, ncat * 3 * sizeof(float), stream>>>(B, m, posed, verts, partials, joints,
+                                                                    smpl_joints, joints_h36m);
+        DANET_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+extern "C" int danet_rot6d_to_rotmat(int32_t n, const float* x, float* R, danet_stream_t s) {
+    DANET_CHECK(n >= 0 && (n == 0 || (x && R)), "danet_rot6d_to_rotmat: bad arguments");
+    if (n == 0) return 0;
+    k_rot6d<<<cdiv(n, 128), 128, 0, (cudaStream_t)s>>>(n, x, R);
+    DANET_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int danet_batch_rodrigues(int32_t n, const float* aa, float* R, int32_t flavor, danet_stream_t s) {
+    DANET_CHECK(n >= 0 && (n == 0 || (aa && R)), "danet_batch_rodrigues: bad arguments");
+    DANET_CHECK(flavor == 0 || flavor == 1, "danet_batch_rodrigues: flavor must be 0 (quaternion) or 1 (smplx)");
+    if (n == 0) return 0;
+    k_rodrigues<<<cdiv(n, 128), 128, 0, (cudaStream_t)s>>>(n, aa, R, flavor);
+    DANET_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int danet_perspective_projection(int32_t B, int32_t N, const float* points, const float* rotation,
+                                            const float* translation, const float* focal, const float* center,
+                                            float* out, danet_stream_t s) {
+    DANET_CHECK(B >= 0 && N >= 0, "danet_perspective_projection: negative size");
+    if (B * N == 0) return 0;
+    DANET_CHECK(points && rotation && translation && focal && center && out, "danet_perspective_projection: null pointer");
+    k_persp<<<cdiv(B * N, 256), 256, 0, (cudaStream_t)s>>>(B, N, points, rotation, translation, focal, center, out);
+    DANET_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int danet_mpjpe_h36m(int32_t B, const float* pred_j17, const float* gt_j14, float* mpjpe, danet_stream_t s) {
+    DANET_CHECK(B >= 0, "danet_mpjpe_h36m: negative batch");
+    if (B == 0) return 0;
+    DANET_CHECK(pred_j17 && gt_j14 && mpjpe, "danet_mpjpe_h36m: null pointer");
+    k_mpjpe<<<cdiv(B, 64), 64, 0, (cudaStream_t)s>>>(B, pred_j17, gt_j14, mpjpe);
+    DANET_LAUNCH_CHECK();
+    return 0;
+}

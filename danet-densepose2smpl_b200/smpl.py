@@ -1,0 +1,286 @@
+"""SMPL layer with the reference's call surface (models/smpl.py:15-46 on top of smplx.SMPL),
+executed by the fused CUDA kernels in csrc/lbs.cu through the C ABI.
+
+    smpl = SMPL(model_dir, batch_size=B, create_transl=False).to(device)
+    out = smpl(betas=betas, body_pose=rotmat[:, 1:], global_orient=rotmat[:, 0:1], pose2rot=False)
+    out.vertices, out.joints, out.joints_J19, out.smpl_joints, ...
+
+Inference only (the reference's hot path runs under torch.no_grad, danet.py:15-28).
+"""
+import ctypes
+import os
+import pickle
+from collections import namedtuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from . import constants
+
+# smplx.body_models.ModelOutput fields (smplx ~0.1.13) + the two the reference adds (models/smpl.py:24)
+ModelOutput_ = namedtuple(
+    "ModelOutput_", ["vertices", "joints", "full_pose", "betas", "global_orient", "body_pose",
+                     "expression", "left_hand_pose", "right_hand_pose", "jaw_pose",
+                     "smpl_joints", "joints_J19"])
+ModelOutput_.__new__.__defaults__ = (None,) * len(ModelOutput_._fields)
+
+
+class _ChStub(object):
+    """Stand-in for chumpy.Ch objects inside the official SMPL pickles (chumpy is not required)."""
+
+    def __setstate__(self, state):
+        self.__dict__.update(state if isinstance(state, dict) else {"x": state})
+
+    def as_array(self):
+        for k in ("x", "r", "_x"):
+            if k in self.__dict__:
+                return np.asarray(self.__dict__[k])
+        raise ValueError("cannot recover the array of a chumpy object with keys %s" % list(self.__dict__))
+
+
+class _SmplUnpickler(pickle.Unpickler):
+    def find_class(self, module, name):
+        if module.startswith("chumpy"):
+            return _ChStub
+        return super().find_class(module, name)
+
+
+def _arr(v):
+    if isinstance(v, _ChStub):
+        return v.as_array()
+    if hasattr(v, "toarray"):          # scipy.sparse J_regressor
+        return v.toarray()
+    return np.asarray(v)
+
+
+def load_smpl_model(model_path, gender="neutral"):
+    """dict of numpy arrays from (a) a dict (already loaded / synthetic), (b) an .npz written by
+    `save_smpl_npz`, (c) the official SMPL_{GENDER}.pkl or a directory containing it
+    (models/smpl.py -> smplx.SMPL.__init__; path_config.py:65 SMPL_MODEL_DIR = 'data/smpl')."""
+    if isinstance(model_path, dict):
+        return model_path
+    if os.path.isdir(model_path):
+        model_path = os.path.join(model_path, "SMPL_%s.pkl" % gender.upper())
+    if not os.path.exists(model_path):
+        raise ValueError("SMPL model file %s does not exist" % model_path)
+    if model_path.endswith(".npz"):
+        z = np.load(model_path)
+        return {k: z[k] for k in z.files}
+    with open(model_path, "rb") as f:
+        raw = _SmplUnpickler(f, encoding="latin1").load()
+    shapedirs = _arr(raw["shapedirs"])[:, :, :10]
+    posedirs = _arr(raw["posedirs"])                      # [6890, 3, 207]
+    parents = _arr(raw["kintree_table"])[0].astype(np.int64).copy()
+    parents[0] = -1
+    return {"v_template": _arr(raw["v_template"]).astype(np.float32),
+            "shapedirs": shapedirs.astype(np.float32),
+            "posedirs": posedirs.reshape(-1, posedirs.shape[-1]).T.astype(np.float32),   # smplx: [207, 20670]
+            "J_regressor": _arr(raw["J_regressor"]).astype(np.float32),
+            "lbs_weights": _arr(raw["weights"]).astype(np.float32),
+            "parents": parents.astype(np.int32),
+            "faces": _arr(raw["f"]).astype(np.int64)}
+
+
+def _maybe_load(x, default_path):
+    if x is None:
+        x = default_path
+    if isinstance(x, str):
+        if not os.path.exists(x):
+            raise ValueError("%s does not exist" % x)
+        return np.load(x)
+    return np.asarray(x)
+
+
+class SMPL(nn.Module):
+    """Extension of SMPL to 49 joints -- same constructor / call surface as models/smpl.py."""
+
+    NUM_JOINTS = 23
+    NUM_BODY_JOINTS = 23
+    NUM_BETAS = 10
+
+    def __init__(self, model_path, gender="neutral", batch_size=1, create_transl=False,
+                 J_regressor_extra=None, J_regressor_h36m=None, dtype=torch.float32, **kwargs):
+        super().__init__()
+        m = load_smpl_model(model_path, gender)
+        self.gender = gender
+        self.batch_size = batch_size
+        self.dtype = dtype
+        self.faces = np.asarray(m["faces"])                                   # ndarray [13776,3] (part_utils.py:22)
+        f32 = lambda a: torch.tensor(np.asarray(a), dtype=torch.float32)
+        self.register_buffer("faces_tensor", torch.tensor(self.faces.astype(np.int64)))
+        self.register_buffer("v_template", f32(m["v_template"]))
+        self.register_buffer("shapedirs", f32(m["shapedirs"]))
+        self.register_buffer("posedirs", f32(m["posedirs"]))
+        self.register_buffer("J_regressor", f32(m["J_regressor"]))
+        self.register_buffer("lbs_weights", f32(m["lbs_weights"]))
+        self.register_buffer("parents", torch.tensor(np.asarray(m["parents"]).astype(np.int64)))
+        # models/smpl.py:21-22 (path_config.py:64 JOINT_REGRESSOR_TRAIN_EXTRA)
+        extra = m["J_regressor_extra"] if (J_regressor_extra is None and "J_regressor_extra" in m) else \
+            _maybe_load(J_regressor_extra, "data/J_regressor_extra.npy")
+        self.register_buffer("J_regressor_extra", f32(extra))
+        # eval.py:78 (path_config.py:66 JOINT_REGRESSOR_H36M) -- optional, fused into the same pass
+        if J_regressor_h36m is None and "J_regressor_h36m" in m:
+            J_regressor_h36m = m["J_regressor_h36m"]
+        elif J_regressor_h36m is None and os.path.exists("data/J_regressor_h36m.npy"):
+            J_regressor_h36m = np.load("data/J_regressor_h36m.npy")
+        if J_regressor_h36m is not None:
+            self.register_buffer("J_regressor_h36m", f32(_maybe_load(J_regressor_h36m, None)))
+        else:
+            self.J_regressor_h36m = None
+        self.selected_verts = np.asarray(m.get("selected_verts", constants.SMPLX_SELECTED_VERTS), dtype=np.int32)
+        self.joint_map = torch.tensor(constants.JOINT_MAP_49, dtype=torch.long)       # models/smpl.py:23
+        self.ModelOutput = ModelOutput_
+        self._handles = {}
+        self._ws = {}
+        self.last_joints_h36m = None
+
+    # -- C-ABI handle per device ------------------------------------------------------------
+    def _handle(self, device):
+        key = device.index if device.index is not None else torch.cuda.current_device()
+        if key in self._handles:
+            return self._handles[key]
+        lib = _lib.load()
+        keep = []
+
+        def host(t, dt):
+            a = np.ascontiguousarray(t.detach().cpu().numpy() if torch.is_tensor(t) else np.asarray(t), dtype=dt)
+            keep.append(a)
+            return a.ctypes.data_as(ctypes.c_void_p)
+
+        d = _lib.SmplDesc()
+        d.num_verts = self.v_template.shape[0]
+        d.num_joints = self.J_regressor.shape[0]
+        d.num_betas = self.shapedirs.shape[-1]
+        d.v_template = host(self.v_template, np.float32)
+        d.shapedirs = host(self.shapedirs, np.float32)
+        d.posedirs = host(self.posedirs, np.float32)
+        d.J_regressor = host(self.J_regressor, np.float32)
+        d.lbs_weights = host(self.lbs_weights, np.float32)
+        d.parents = host(self.parents, np.int32)
+        d.num_selected = len(self.selected_verts)
+        d.selected_verts = host(self.selected_verts, np.int32)
+        d.num_extra = self.J_regressor_extra.shape[0]
+        d.J_regressor_extra = host(self.J_regressor_extra, np.float32)
+        if self.J_regressor_h36m is not None:
+            d.num_h36m = self.J_regressor_h36m.shape[0]
+            d.J_regressor_h36m = host(self.J_regressor_h36m, np.float32)
+        else:
+            d.num_h36m = 0
+            d.J_regressor_h36m = None
+        d.num_out_joints = len(self.joint_map)
+        d.joint_map = host(self.joint_map, np.int32)
+        h = ctypes.c_void_p()
+        with torch.cuda.device(key):
+            _lib.check(lib.danet_smpl_create(ctypes.byref(d), ctypes.byref(h)), "smpl_create")
+        self._handles[key] = h
+        return h
+
+    def __del__(self):
+        try:
+            lib = _lib.load()
+            for h in self._handles.values():
+                lib.danet_smpl_destroy(h)
+        except Exception:
+            pass
+
+    def _workspace(self, h, B, device):
+        need = _lib.load().danet_smpl_workspace_bytes(h, B)
+        key = (device.index, )
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(int(need), dtype=torch.uint8, device=device)
+            self._ws[key] = ws
+        return ws
+
+    # -- forward ----------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, betas=None, body_pose=None, global_orient=None, transl=None, return_verts=True,
+                return_full_pose=False, pose2rot=True, pose6d=None, bodies_per_cta=0, **kwargs):
+        """betas [B,10]; body_pose [B,23,3,3] | [B,69]; global_orient [B,1,3,3] | [B,3].
+        `pose6d` [B,24,6] (extension): feed the network's 6-d output directly (rot6d front-end)."""
+        dev = self.v_template.device
+        if dev.type != "cuda":
+            raise RuntimeError("danet_b200.SMPL: move the module to a CUDA device first (no CPU path)")
+        B = None
+        for t in (betas, body_pose, global_orient, pose6d):
+            if t is not None:
+                B = t.shape[0]
+                break
+        if B is None:
+            B = self.batch_size
+        f = lambda t: t.to(device=dev, dtype=torch.float32).contiguous()
+        betas = torch.zeros(B, self.shapedirs.shape[-1], device=dev) if betas is None else f(betas)
+        if pose6d is not None:
+            pose = f(pose6d).reshape(B, 24, 6)
+            kind = 2
+            go_in, bp_in = None, None
+        elif pose2rot:
+            go = torch.zeros(B, 3, device=dev) if global_orient is None else f(global_orient).reshape(B, 3)
+            bp = torch.zeros(B, 69, device=dev) if body_pose is None else f(body_pose).reshape(B, 69)
+            pose = torch.cat([go, bp], dim=1).contiguous()
+            kind = 1
+            go_in, bp_in = go, bp
+        else:
+            eye = torch.eye(3, device=dev)
+            go = eye.expand(B, 1, 3, 3) if global_orient is None else f(global_orient).reshape(B, 1, 3, 3)
+            bp = eye.expand(B, 23, 3, 3) if body_pose is None else f(body_pose).reshape(B, 23, 3, 3)
+            pose = torch.cat([go, bp], dim=1).contiguous()
+            kind = 0
+            go_in, bp_in = go, bp
+        if betas.shape[0] != B or pose.shape[0] != B:
+            raise ValueError("SMPL.forward: inconsistent batch sizes")
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            h = self._handle(dev)
+            V = self.v_template.shape[0]
+            verts = torch.empty(B, V, 3, device=dev)
+            joints = torch.empty(B, len(self.joint_map), 3, device=dev)
+            smpl_joints = torch.empty(B, 24, 3, device=dev)
+            nh = 0 if self.J_regressor_h36m is None else self.J_regressor_h36m.shape[0]
+            jh = torch.empty(B, nh, 3, device=dev) if nh else None
+            rot = torch.empty(B, 24, 3, 3, device=dev) if kind != 0 else None
+            ws = self._workspace(h, B, dev)
+            _lib.check(lib.danet_smpl_forward(h, B, _lib.ptr(betas), _lib.ptr(pose), kind, _lib.ptr(verts),
+                                              _lib.ptr(joints), _lib.ptr(smpl_joints), _lib.ptr(jh),
+                                              _lib.ptr(rot), _lib.ptr(ws), int(bodies_per_cta),
+                                              _lib.stream_ptr()), "smpl_forward")
+        if transl is not None:
+            joints = joints + transl.unsqueeze(1)
+            verts = verts + transl.unsqueeze(1)
+        self.last_joints_h36m = jh
+        self.last_rotmats = rot if rot is not None else pose
+        joints_J24 = joints[:, -24:, :]
+        joints_J19 = joints_J24[:, constants.J24_TO_J19, :]                      # models/smpl.py:36-37
+        if pose6d is not None:
+            go_in, bp_in = rot[:, :1], rot[:, 1:]
+        full_pose = None
+        if return_full_pose:
+            full_pose = torch.cat([go_in.reshape(B, -1, *go_in.shape[2:]) if kind == 0 else go_in,
+                                   bp_in], dim=1)
+        return self.ModelOutput(vertices=verts if return_verts else None,
+                                global_orient=go_in, body_pose=bp_in, joints=joints,
+                                joints_J19=joints_J19, smpl_joints=smpl_joints, betas=betas,
+                                full_pose=full_pose)
+
+    def joints_h36m(self):
+        """[B,17,3] J_regressor_h36m joints of the last forward (eval.py:186,202 fused into the pass)."""
+        return self.last_joints_h36m
+
+
+def save_smpl_npz(path, model):
+    np.savez(path, **{k: np.asarray(v) for k, v in model.items()})
+
+
+@torch.no_grad()
+def mpjpe_h36m(pred_j17, gt_j14):
+    """eval.py:202-212: pred_j17 [B,17,3] from J_regressor_h36m; gt_j14 [B,14,3] pelvis-centred."""
+    _lib.require_cuda(pred_j17, "pred_j17")
+    B = pred_j17.shape[0]
+    out = torch.empty(B, device=pred_j17.device)
+    with torch.cuda.device(pred_j17.device):
+        _lib.check(_lib.load().danet_mpjpe_h36m(B, _lib.ptr(pred_j17.float().contiguous()),
+                                               _lib.ptr(gt_j14.float().contiguous()), _lib.ptr(out),
+                                               _lib.stream_ptr()), "mpjpe_h36m")
+    return out

@@ -1,0 +1,76 @@
+"""Generates tests/golden/*.npz by running the REFERENCE'S OWN Python code (imported from
+/root/reference with the shims in oracle/ref_import.py).  Run in this container only:
+
+    python -m oracle.gen_golden [geometry] [iuvmap] [net]
+
+The vectors pin the oracle restatements (oracle/lbs.py geometry helpers) and the CUDA kernels."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def gen_geometry(ns):
+    torch = ns.torch
+    g = torch.Generator().manual_seed(1234)
+    x6 = torch.randn(64, 6, generator=g)
+    x6[0] = torch.tensor([1., 0., 0., 1., 0., 0.])          # identity pattern
+    aa = torch.randn(64, 3, generator=g) * 0.7
+    aa[0] = 0.0
+    aa[1] = torch.tensor([3.1, 0.0, 0.0])
+    pts = torch.randn(3, 17, 3, generator=g)
+    pts[..., 2] += 5.0
+    rot = ns.geometry.batch_rodrigues(torch.randn(3, 3, generator=g) * 0.2)
+    tr = torch.randn(3, 3, generator=g) * 0.1
+    ctr = torch.tensor([[112., 112.]] * 3)
+    out = {
+        "x6": x6.numpy(), "rot6d": ns.geometry.rot6d_to_rotmat(x6).numpy(),
+        "aa": aa.numpy(), "rodrigues_quat": ns.geometry.batch_rodrigues(aa).numpy(),
+        "pts": pts.numpy(), "rot": rot.numpy(), "tr": tr.numpy(), "ctr": ctr.numpy(),
+        "persp": ns.geometry.perspective_projection(pts, rot, tr, 5000., ctr).numpy(),
+    }
+    np.savez_compressed(os.path.join(GOLD, "geometry.npz"), **out)
+    print("geometry.npz written")
+
+
+def gen_iuvmap(ns):
+    torch = ns.torch
+    g = torch.Generator().manual_seed(4321)
+    U, V, I = (torch.randn(2, 25, 12, 12, generator=g) for _ in range(3))
+    A = torch.randn(2, 15, 12, 12, generator=g)
+    I[0, :, 0, 0] = 0.5                                   # exact tie -> first index
+    I[0, 3, 0, 1] = I[0, 7, 0, 1] = 9.0                   # tie between 3 and 7
+    cu, cv, ci, ca = ns.iuvmap.iuvmap_clean(U, V, I, A)
+    pu, pv, pi_, _ = ns.iuvmap.iuvmap_clean(U[:, :7], V[:, :7], I[:, :7])
+    part = torch.randint(0, 25, (2, 12, 12), generator=g).float()
+    img = torch.stack([part / 24.0, torch.rand(2, 12, 12, generator=g), torch.rand(2, 12, 12, generator=g)], 1)
+    img[:, 1:] *= (part > 0).float().unsqueeze(1)
+    torch.Tensor.get_device = lambda self: -1 if not self.is_cuda else self.device.index
+    mu, mv, mi, ma = ns.iuvmap.iuv_img2map(img)
+    np.savez_compressed(os.path.join(GOLD, "iuvmap.npz"), U=U.numpy(), V=V.numpy(), I=I.numpy(), A=A.numpy(),
+                        cu=cu.numpy(), cv=cv.numpy(), ci=ci.numpy(), ca=ca.numpy(),
+                        pu=pu.numpy(), pv=pv.numpy(), pi=pi_.numpy(),
+                        img=img.numpy(), mu=mu.numpy(), mv=mv.numpy(), mi=mi.numpy(), ma=ma.numpy())
+    print("iuvmap.npz written")
+
+
+def main():
+    sys.path.insert(0, ROOT)
+    from oracle import ref_import
+    what = sys.argv[1:] or ["geometry", "iuvmap", "net"]
+    ns = ref_import.load(48)
+    os.makedirs(GOLD, exist_ok=True)
+    if "geometry" in what:
+        gen_geometry(ns)
+    if "iuvmap" in what:
+        gen_iuvmap(ns)
+    if "net" in what:
+        from oracle import gen_golden_net
+        gen_golden_net.main(ns)
+
+
+if __name__ == "__main__":
+    main()

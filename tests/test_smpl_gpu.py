@@ -1,0 +1,104 @@
+"""GPU parity: fused SMPL layer (csrc/lbs.cu via the C ABI) vs the CPU oracle.
+Tolerance from BASELINE.json north_star: vertices / joints within 1e-4 abs (fp32)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lbs, synth
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _inputs(B, seed):
+    rng = np.random.default_rng(seed)
+    betas = rng.normal(0, 1, (B, 10)).astype(np.float32)
+    aa = rng.normal(0, 0.3, (B, 72)).astype(np.float32)
+    x6 = rng.normal(0, 1, (B, 24, 6)).astype(np.float32)
+    return betas, aa, x6
+
+
+def _check(out, ref, smpl):
+    assert np.abs(out.vertices.cpu().numpy() - ref["vertices"]).max() < TOL
+    assert np.abs(out.joints.cpu().numpy() - ref["joints"]).max() < TOL
+    assert np.abs(out.smpl_joints.cpu().numpy() - ref["smpl_joints"]).max() < TOL
+    assert np.abs(out.joints_J19.cpu().numpy() - ref["joints_J19"]).max() < TOL
+    assert np.abs(smpl.joints_h36m().cpu().numpy() - ref["joints_h36m"]).max() < TOL
+
+
+@pytest.mark.parametrize("B", [1, 4, 7, 64])
+def test_smpl_axis_angle(smpl_model, B):
+    import danet_b200
+    dev = torch.device("cuda:0")
+    smpl = danet_b200.SMPL(smpl_model, batch_size=B).to(dev)
+    betas, aa, _ = _inputs(B, B)
+    out = smpl(betas=torch.from_numpy(betas).to(dev), body_pose=torch.from_numpy(aa[:, 3:]).to(dev),
+               global_orient=torch.from_numpy(aa[:, :3]).to(dev), pose2rot=True)
+    ref = lbs.smpl_forward(smpl_model, betas, aa[:, 3:], aa[:, :3], pose2rot=True, dtype=np.float64)
+    _check(out, ref, smpl)
+    assert out.vertices.shape == (B, 6890, 3) and out.joints.shape == (B, 49, 3)
+
+
+@pytest.mark.parametrize("nb", [1, 2, 4, 8, 16])
+def test_smpl_rotmat_all_body_blockings(smpl_model, nb):
+    import danet_b200
+    dev = torch.device("cuda:0")
+    B = 19                                   # ragged against every blocking
+    smpl = danet_b200.SMPL(smpl_model).to(dev)
+    betas, aa, x6 = _inputs(B, 100 + nb)
+    R = lbs.rot6d_to_rotmat(x6.reshape(-1, 6)).reshape(B, 24, 3, 3).astype(np.float32)
+    out = smpl(betas=torch.from_numpy(betas).to(dev), body_pose=torch.from_numpy(R[:, 1:]).to(dev),
+               global_orient=torch.from_numpy(R[:, :1]).to(dev), pose2rot=False, bodies_per_cta=nb)
+    ref = lbs.smpl_forward(smpl_model, betas, R[:, 1:], R[:, :1], pose2rot=False, dtype=np.float64)
+    _check(out, ref, smpl)
+
+
+def test_smpl_rot6d_frontend_and_dense_weights():
+    import danet_b200
+    dev = torch.device("cuda:0")
+    model = synth.make_smpl_model(5, dense_weights=True)     # exercises the dense skinning path
+    smpl = danet_b200.SMPL(model).to(dev)
+    B = 5
+    betas, _, x6 = _inputs(B, 7)
+    out = smpl(betas=torch.from_numpy(betas).to(dev), pose6d=torch.from_numpy(x6).to(dev))
+    R = lbs.rot6d_to_rotmat(x6.reshape(-1, 6).astype(np.float64)).reshape(B, 24, 3, 3)
+    ref = lbs.smpl_forward(model, betas, R[:, 1:], R[:, :1], pose2rot=False, dtype=np.float64)
+    _check(out, ref, smpl)
+
+
+def test_smpl_rest_pose_is_template_plus_shape(smpl_model):
+    import danet_b200
+    dev = torch.device("cuda:0")
+    smpl = danet_b200.SMPL(smpl_model, batch_size=2).to(dev)
+    out = smpl()                                               # all defaults -> zeros, like smplx
+    np.testing.assert_allclose(out.vertices[0].cpu().numpy(), smpl_model["v_template"], atol=1e-6)
+    betas = torch.randn(2, 10, device=dev)
+    out = smpl(betas=betas, pose2rot=False)
+    vs = smpl_model["v_template"][None] + np.einsum("bl,mkl->bmk", betas.cpu().numpy(), smpl_model["shapedirs"])
+    np.testing.assert_allclose(out.vertices.cpu().numpy(), vs, atol=1e-5)
+
+
+def test_smpl_large_batch_property(smpl_model):
+    """Full-size batch: linearity property instead of the (slow) oracle -- with identity pose the
+    vertices are affine in beta: v(b1)+v(b2)-v(0) == v(b1+b2)."""
+    import danet_b200
+    dev = torch.device("cuda:0")
+    smpl = danet_b200.SMPL(smpl_model).to(dev)
+    B = 4096
+    g = torch.Generator(device="cpu").manual_seed(0)
+    b1 = torch.randn(B, 10, generator=g).to(dev)
+    b2 = torch.randn(B, 10, generator=g).to(dev)
+    v = lambda b: smpl(betas=b, pose2rot=False).vertices
+    lhs = v(b1) + v(b2) - v(torch.zeros_like(b1))
+    assert (lhs - v(b1 + b2)).abs().max().item() < 1e-4
+
+
+def test_mpjpe_kernel(smpl_model):
+    import danet_b200
+    from danet_b200.smpl import mpjpe_h36m
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(0)
+    j17 = rng.normal(0, 0.3, (9, 17, 3)).astype(np.float32)
+    gt = rng.normal(0, 0.3, (9, 14, 3)).astype(np.float32)
+    got = mpjpe_h36m(torch.from_numpy(j17).to(dev), torch.from_numpy(gt).to(dev)).cpu().numpy()
+    np.testing.assert_allclose(got, lbs.mpjpe_h36m(j17.astype(np.float64), gt), atol=1e-6)

@@ -6,3 +6,5 @@ from . import constants  # noqa: F401
 from .smpl import SMPL, ModelOutput_, mpjpe_h36m  # noqa: F401
 from .renderer import IUV_Renderer  # noqa: F401
 from . import geometry, iuvmap  # noqa: F401
+from .danet import DaNet, build_synthetic_danet  # noqa: F401
+from . import synthetic  # noqa: F401

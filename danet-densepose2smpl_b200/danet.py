@@ -1,0 +1,195 @@
+"""DaNet with the reference's call surface (models/danet/danet.py:31-131):
+
+    model = DaNet(options, smpl_mean_params, pretrained=False).to(device)
+    model.load_state_dict(checkpoint['model'], strict=False); model.eval()
+    pred = model.infer_net(image)            # {'para': [B,229], 'visualization': {...}}
+
+Parameters live under the reference's state_dict key names (img2iuv.iuv_est.*,
+img2iuv.learned_{ratio,offset}, iuv2smpl.smpl_para_Outs.*, iuv2smpl.smpl.*); the forward is an
+execution plan over the CUDA kernels of libdanet_b200.so (plan.py), not torch modules.
+"""
+import math
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import constants
+from . import netgraph as ng
+from .plan import Plan
+from .renderer import IUV_Renderer
+from .smpl import SMPL
+
+# configs/danet_default.yaml values the inference path reads
+DEFAULT_CFG = dict(INIMG_SIZE=224, HEATMAP_SIZE=56, STN_PART_VIS_SCORE=0.5, WIDTH=48,
+                   PRETRAINED_COCO="data/pretrained_model/pose_hrnet_w48_256x192.pth",
+                   PRETRAINED_18="data/pretrained_model/resnet18-5c106cde.pth",
+                   SMPL_MODEL_DIR="data/smpl")
+
+
+class ParamTree(nn.Module):
+    """Container that registers tensors under dotted reference key names."""
+
+    def add(self, key, tensor, kind="param"):
+        head, _, rest = key.partition(".")
+        if rest:
+            if head not in self._modules:
+                self.add_module(head, ParamTree())
+            self._modules[head].add(rest, tensor, kind)
+        elif kind == "param":
+            self.register_parameter(head, nn.Parameter(tensor, requires_grad=tensor.is_floating_point()))
+        else:
+            self.register_buffer(head, tensor)
+
+
+def _init_tensor(spec, mean_params, gbuf):
+    shape, init = spec.shape, spec.init
+    if init == "ones":
+        return torch.ones(shape)
+    if init == "zeros":
+        return torch.zeros(shape)
+    if init == "long0":
+        return torch.zeros(shape, dtype=torch.long)
+    if init == "conv" or init == "linear":
+        fan_in = int(np.prod(shape[1:]))
+        return (torch.rand(shape) * 2 - 1) / math.sqrt(fan_in)
+    if init.startswith("conv_bias:"):
+        return (torch.rand(shape) * 2 - 1) / math.sqrt(int(init.split(":")[1]))
+    if init == "xavier_relu":
+        bound = math.sqrt(2.0) * math.sqrt(6.0 / (shape[0] + shape[1]))
+        return (torch.rand(shape) * 2 - 1) * bound
+    if init == "xavier_small":
+        bound = 0.01 * math.sqrt(6.0 / (shape[0] + shape[1]))
+        return (torch.rand(shape) * 2 - 1) * bound
+    if init == "learned_ratio":
+        return torch.from_numpy(constants.LEARNED_RATIO.copy())
+    if init == "learned_offset":
+        return torch.from_numpy(constants.LEARNED_OFFSET.copy())
+    if init == "mean_cam_shape":
+        return torch.cat([torch.as_tensor(mean_params["cam"], dtype=torch.float32).reshape(1, 3),
+                          torch.as_tensor(mean_params["shape"], dtype=torch.float32).reshape(1, 10)], dim=1)
+    if init == "mean_pose":
+        return torch.as_tensor(mean_params["pose"], dtype=torch.float32).reshape(1, 144)
+    if init.startswith("graph:"):
+        return torch.from_numpy(gbuf[init.split(":")[1]].copy())
+    raise ValueError(init)
+
+
+def load_mean_params(smpl_mean_params):
+    if isinstance(smpl_mean_params, dict):
+        return smpl_mean_params
+    if not os.path.exists(smpl_mean_params):
+        raise ValueError("%s does not exist (smpl_mean_params, reference README.md:44-48)" % smpl_mean_params)
+    z = np.load(smpl_mean_params)
+    return {k: z[k] for k in ("pose", "shape", "cam")}
+
+
+class DaNet(nn.Module):
+    """Decompose-and-aggregate network, inference path (INPUT_MODE='iuv', DECOMPOSED, 'gcn')."""
+
+    def __init__(self, options, smpl_mean_params, pretrained=True, width=None, smpl_model=None, dp_mesh=None,
+                 conv_algo="auto", legacy_align_corners=False, cfg=None, use_cuda_graph=False, want_vis=True):
+        super().__init__()
+        self.options = options
+        self.cfg = dict(DEFAULT_CFG)
+        if cfg:
+            self.cfg.update(cfg)
+        self.width = width or self.cfg["WIDTH"]
+        self.conv_algo = conv_algo
+        self.legacy_align_corners = legacy_align_corners
+        self.use_cuda_graph = use_cuda_graph
+        self.want_vis = want_vis
+        self.graph = ng.danet_graph(self.width, self.cfg["INIMG_SIZE"])
+        mean_params = load_mean_params(smpl_mean_params)
+        gbuf = ng.graph_buffers()
+        self.img2iuv = ParamTree()
+        self.iuv2smpl = ParamTree()
+        for key, spec in self.graph.params.items():
+            root, rest = key.split(".", 1)
+            getattr(self, root).add(rest, _init_tensor(spec, mean_params, gbuf), spec.kind)
+        self.img2iuv.dp2smpl_mapping = constants.DP2SMPL_MAPPING                    # demo.py:139
+        bs = getattr(options, "batch_size", 1) if options is not None else 1
+        self.iuv2smpl.smpl = SMPL(smpl_model if smpl_model is not None else self.cfg["SMPL_MODEL_DIR"],
+                                  batch_size=bs, create_transl=False)                   # smpl_regressor.py:64
+        self.iuv_renderer = IUV_Renderer(self.cfg["INIMG_SIZE"], self.cfg["HEATMAP_SIZE"], mesh=dp_mesh)  # danet.py:59
+        self._plans = {}
+        if pretrained:
+            self._load_pretrained()
+        self.train()                                     # nn.Module default; callers call .eval()
+
+    # -- pretrained backbones (iuv_estimator.py:46-54, smpl_regressor.py:438-439,501-502) --------
+    def _load_pretrained(self):
+        hr = self.cfg["PRETRAINED_COCO"]
+        if not os.path.isfile(hr):
+            raise ValueError("{} is not exist!".format(hr))                           # hr_module.py:408-410
+        sd = torch.load(hr, map_location="cpu")
+        self.img2iuv.iuv_est.load_state_dict(sd, strict=False)
+        r18 = self.cfg["PRETRAINED_18"]
+        if not os.path.isfile(r18):
+            raise ValueError("imagenet pretrained model does not exist")             # res_module.py:493-497
+        sd = torch.load(r18, map_location="cpu")
+        for net in (self.iuv2smpl.smpl_para_Outs.body_net._modules["3"], self.iuv2smpl.smpl_para_Outs.limb_net._modules["3"]):
+            own = net.state_dict()
+            net.load_state_dict({k: v for k, v in sd.items() if k in own and own[k].shape == v.shape}, strict=False)
+
+    # -- plan cache -----------------------------------------------------------------------------
+    def _apply(self, fn, *a, **k):
+        self._plans = {}
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        self._plans = {}
+        return super().load_state_dict(state_dict, strict=strict, **kw)
+
+    def _algo(self):
+        if self.conv_algo == "auto":
+            return "tc"
+        return self.conv_algo
+
+    def plan_for(self, B, device, ops=None):
+        key = (B, str(device))
+        if key not in self._plans:
+            sd = {k: v for k, v in self.state_dict().items() if not k.startswith("iuv2smpl.smpl.")}
+            self._plans[key] = Plan(self.graph, sd, B, device, conv_algo=self._algo(),
+                                    align_corners=self.legacy_align_corners,
+                                    vis_thresh=self.cfg["STN_PART_VIS_SCORE"], want_vis=self.want_vis, ops=ops,
+                                    use_cuda_graph=self.use_cuda_graph)
+        return self._plans[key]
+
+    # -- inference ------------------------------------------------------------------------------
+    @torch.no_grad()
+    def infer_net(self, image):
+        """image [B,3,224,224] fp32 -> {'para': [B,229] = cam(3)|shape(10)|24 rot-mats, 'visualization': ...}"""
+        if self.training:
+            raise ValueError('You should call this function only on inference.'
+                             'Set the network in inference mode by net.eval().')        # danet.py:24-26
+        dev = self.img2iuv.learned_ratio.device
+        if dev.type != "cuda" and not getattr(self, "_test_ops", None):
+            raise RuntimeError("danet_b200.DaNet: move the model to a CUDA device (there is no CPU path)")
+        B = image.shape[0]
+        plan = self.plan_for(B, dev, ops=getattr(self, "_test_ops", None))
+        plan.run(image)
+        S = self.cfg["HEATMAP_SIZE"]
+        ret = {"visualization": {}}
+        ret["para"] = plan.out("para").reshape(-1)[:B * 229].view(B, 229).clone()
+        if plan.vis is not None:
+            ret["visualization"]["iuv_pred"] = [t.clone() for t in plan.vis]
+            ret["visualization"]["part_iuv_pred"] = plan.raw_parts.view(B, 24, 3, 7, S, S).clone()
+        ret["stn_kps_pred"] = plan.out("centers").reshape(-1)[:B * 48].view(B, 24, 2).clone()
+        return ret
+
+    def forward(self, in_dict):
+        raise NotImplementedError("danet_b200.DaNet implements the inference path (infer_net); the training "
+                                  "forward (danet.py:133-366) is out of scope (SURVEY section 8f)")
+
+
+def build_synthetic_danet(width=48, seed=0, device="cuda:0", conv_algo="auto", keyed=True, **kw):
+    """Random-weight DaNet on synthetic assets (no licensed files / checkpoints needed)."""
+    from . import synthetic
+    net = DaNet(None, synthetic.make_mean_params(seed), pretrained=False, width=width,
+                smpl_model=synthetic.make_smpl_model(seed), dp_mesh=synthetic.make_dp_mesh(seed),
+                conv_algo=conv_algo, **kw)
+    if keyed:
+        net.load_state_dict(synthetic.keyed_state_dict(net.state_dict(), seed), strict=True)
+    return net.to(device).eval()

@@ -1,0 +1,168 @@
+"""GPU unit parity of the network-half kernels (csrc/conv_simt.cu, conv_tc.cu, glue.cu) against a
+plain torch fp32 reference of the same op (tests/emul_ops.py restates each op with torch)."""
+import numpy as np
+import pytest
+import torch
+
+from emul_ops import TorchEmulOps
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _ops():
+    from danet_b200.plan import CudaOps
+    return CudaOps(DEV)
+
+
+CONV_CASES = [
+    # N, H, W, Cin, Cout, k, stride, wsets, relu, residual
+    (2, 56, 56, 48, 48, 3, 1, 1, 1, 1),
+    (2, 28, 28, 96, 96, 3, 1, 1, 1, 1),
+    (3, 14, 14, 192, 192, 3, 1, 1, 0, 0),
+    (2, 7, 7, 384, 384, 3, 1, 1, 1, 1),
+    (2, 56, 56, 64, 256, 1, 1, 1, 1, 1),
+    (2, 56, 56, 256, 64, 1, 1, 1, 1, 0),
+    (2, 56, 56, 48, 96, 3, 2, 1, 0, 0),
+    (1, 224, 224, 4, 64, 3, 2, 1, 1, 0),
+    (2, 56, 56, 64, 64, 7, 2, 1, 1, 0),
+    (48, 56, 56, 48, 24, 3, 1, 24, 0, 0),
+    (48, 4, 4, 256, 128, 3, 2, 24, 1, 0),
+    (48, 4, 4, 256, 128, 1, 2, 24, 0, 0),
+    (2, 56, 56, 48, 92, 3, 1, 1, 0, 0),
+    (2, 56, 56, 76, 64, 1, 1, 1, 1, 0),
+    (5, 13, 9, 20, 36, 3, 1, 1, 1, 1),          # ragged: nothing divides the tile sizes
+    (2, 14, 14, 64, 64, 3, 1, 1, 1, 1),
+    (2, 28, 28, 64, 128, 3, 2, 1, 1, 0),
+    (2, 28, 28, 64, 128, 1, 2, 1, 0, 0),
+]
+
+
+def _conv_case(case, algo, tol):
+    N, H, W, Cin, Cout, k, s, G, relu, has_res = case
+    ops, ref = _ops(), TorchEmulOps()
+    g = torch.Generator().manual_seed(hash(case) & 0xFFFF)
+    d = dict(N=N, H=H, W=W, Cin=Cin, Cout=Cout, ksize=k, stride=s, pad=k // 2, wsets=G, relu=relu)
+    Ho, Wo = (H + 2 * (k // 2) - k) // s + 1, (W + 2 * (k // 2) - k) // s + 1
+    x = torch.randn(N, H, W, Cin, generator=g)
+    w = torch.randn(G, k * k * Cin, Cout, generator=g) * (1.0 / (k * k * Cin)) ** 0.5
+    b = torch.randn(G, Cout, generator=g) * 0.1
+    res = torch.randn(N, Ho, Wo, Cout, generator=g) if has_res else None
+    y_ref = torch.empty(N, Ho, Wo, Cout)
+    ref.conv2d(d, 0, x, w, b, res, y_ref)
+    xc, wc, bc = x.to(DEV), w.to(DEV), b.to(DEV)
+    rc = res.to(DEV) if has_res else None
+    y = torch.full((N, Ho, Wo, Cout), float("nan"), device=DEV)
+    if algo == 1:
+        if not ops.conv_tc_supported(d):
+            pytest.skip("shape not on the tcgen05 path")
+        wc = ops.conv_tc_pack(d, wc)
+    ops.conv2d(d, algo, xc, wc, bc, rc, y)
+    torch.cuda.synchronize()
+    err = (y.cpu() - y_ref).abs().max().item()
+    assert err < tol, (case, err)
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_simt(case):
+    _conv_case(case, 0, 2e-5)
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_tc(case):
+    # TF32 operands (10-bit mantissa), fp32 accumulate: |err| <= ~2^-10 * sum|a||b| ~ 3e-3 at unit scale
+    _conv_case(case, 1, 6e-3)
+
+
+def test_conv_rejects_bad_arguments():
+    ops = _ops()
+    d = dict(N=1, H=8, W=8, Cin=3, Cout=8, ksize=3, stride=1, pad=1, wsets=1, relu=0)
+    x = torch.zeros(1, 8, 8, 3, device=DEV)
+    with pytest.raises(RuntimeError):
+        ops.conv2d(d, 0, x, x, None, None, x)        # Cin % 4 != 0
+
+
+def test_glue_kernels_vs_torch():
+    ops, ref = _ops(), TorchEmulOps()
+    g = torch.Generator().manual_seed(7)
+    B, S, C = 3, 56, 48
+    # fuse_sum with upsampling
+    t0, t1, t2 = torch.randn(B, 28, 28, C, generator=g), torch.randn(B, 14, 14, C, generator=g), torch.randn(B, 7, 7, C, generator=g)
+    y_ref = torch.empty(B, 28, 28, C); ref.fuse_sum([t0, t1, t2], [1, 2, 4], True, y_ref)
+    y = torch.empty(B, 28, 28, C, device=DEV); ops.fuse_sum([t0.to(DEV), t1.to(DEV), t2.to(DEV)], [1, 2, 4], True, y)
+    assert torch.equal(y.cpu(), y_ref)
+    # maxpool / avgpool / linear / nchw->nhwc
+    x = torch.randn(B, 28, 28, 64, generator=g)
+    y_ref = torch.empty(B, 14, 14, 64); ref.maxpool(x, y_ref)
+    y = torch.empty(B, 14, 14, 64, device=DEV); ops.maxpool(x.to(DEV), y)
+    assert torch.equal(y.cpu(), y_ref)
+    x = torch.randn(B, 2, 2, 512, generator=g)
+    y_ref = torch.empty(B, 512); ref.avgpool(x, y_ref)
+    y = torch.empty(B, 512, device=DEV); ops.avgpool(x.to(DEV), y)
+    assert (y.cpu() - y_ref).abs().max() < 1e-6
+    w, b, add = torch.randn(13, 512, generator=g), torch.randn(13, generator=g), torch.randn(13, generator=g)
+    o_ref = torch.empty(B, 13); ref.linear(y_ref, w, b, add, o_ref)
+    o = torch.empty(B, 13, device=DEV); ops.linear(y, w.to(DEV), b.to(DEV), add.to(DEV), o)
+    assert (o.cpu() - o_ref).abs().max() < 1e-4
+    img = torch.randn(B, 3, 20, 20, generator=g)
+    n_ref = torch.empty(B, 20, 20, 4); ref.nchw_to_nhwc(img, n_ref)
+    n = torch.empty(B, 20, 20, 4, device=DEV); ops.nchw_to_nhwc(img.to(DEV), n)
+    assert torch.equal(n.cpu(), n_ref)
+
+
+def test_clean_and_stn_kernels_vs_torch():
+    ops, ref = _ops(), TorchEmulOps()
+    g = torch.Generator().manual_seed(8)
+    B, S, C = 3, 56, 48
+    heads = torch.randn(B, S, S, 92, generator=g)
+    heads[0, 0, 0, 50:75] = 1.0                      # exact tie -> first index
+    body_r, amax_r = torch.empty(B, S, S, 76), torch.empty(B, S, S, dtype=torch.uint8)
+    vis_r = [torch.empty(B, c, S, S) for c in (25, 25, 25, 15)]
+    ref.clean_global(heads, body_r, amax_r, vis_r)
+    body, amax = torch.empty(B, S, S, 76, device=DEV), torch.empty(B, S, S, dtype=torch.uint8, device=DEV)
+    vis = [torch.empty(B, c, S, S, device=DEV) for c in (25, 25, 25, 15)]
+    ops.clean_global(heads.to(DEV), body, amax, vis)
+    assert torch.equal(amax.cpu(), amax_r) and torch.equal(body.cpu(), body_r)
+    for a, b in zip(vis, vis_r):
+        assert torch.equal(a.cpu(), b)
+    x = torch.randn(B * 24, S, S, 24, generator=g)
+    y_r, raw_r = torch.empty(B * 24, S, S, 24), torch.empty(B * 24, 21, S, S)
+    ref.clean_parts(x, y_r, raw_r)
+    y, raw = torch.empty(B * 24, S, S, 24, device=DEV), torch.empty(B * 24, 21, S, S, device=DEV)
+    ops.clean_parts(x.to(DEV), y, raw)
+    assert torch.equal(y.cpu(), y_r) and torch.equal(raw.cpu(), raw_r)
+    # stn params + sampling, both align_corners conventions
+    hm = torch.randn(B, S, S, 24, generator=g) * 0.3
+    ratio, offset = torch.rand(24, generator=g) + 0.5, torch.rand(24, generator=g) * 0.2
+    xd = torch.randn(B, S, S, C, generator=g)
+    for ac in (0, 1):
+        c_r, th_r = torch.empty(B, 1, 24, 2), torch.empty(B, 1, 24, 3)
+        ref.stn_params(hm, amax_r, ratio, offset, 0.5, ac, c_r, th_r)
+        c, th = torch.empty(B, 1, 24, 2, device=DEV), torch.empty(B, 1, 24, 3, device=DEV)
+        ops.stn_params(hm.to(DEV), amax, ratio.to(DEV), offset.to(DEV), 0.5, ac, c, th)
+        assert (c.cpu() - c_r).abs().max() < 2e-5 and (th.cpu() - th_r).abs().max() < 2e-5
+        crops_r = torch.empty(B * 24, S, S, C); ref.stn_sample(xd, th_r, ac, crops_r)
+        crops = torch.empty(B * 24, S, S, C, device=DEV); ops.stn_sample(xd.to(DEV), th_r.to(DEV), ac, crops)
+        assert (crops.cpu() - crops_r).abs().max() < 2e-4
+
+
+def test_gcn_pose_head_vs_torch():
+    from danet_b200 import netgraph as ng
+    ops, ref = _ops(), TorchEmulOps()
+    g = torch.Generator().manual_seed(9)
+    B = 5
+    gb = ng.graph_buffers()
+    adj = torch.stack([torch.from_numpy(gb["r2p_A"][0]), torch.from_numpy(ng.undigraph_normalize(gb["A_mask"][0] + np.eye(24)).astype(np.float32)),
+                       torch.from_numpy(gb["p2r_A"][0])]).float()
+    dims = [(128, 128), (128, 256), (256, 256), (256, 128), (128, 128)]
+    gp = {"adj": adj, "W": [torch.randn(i, o, generator=g) * (1.0 / i) ** 0.5 for i, o in dims],
+          "b": [torch.randn(o, generator=g) * 0.1 for _, o in dims],
+          "bn_scale": [torch.rand(24, generator=g) + 0.5 for _ in dims], "bn_shift": [torch.randn(24, generator=g) * 0.1 for _ in dims],
+          "head_w": torch.randn(144, 128, generator=g) * 0.1, "head_b": torch.randn(144, generator=g) * 0.1,
+          "mean_pose": torch.tensor([1., 0, 0, 1, 0, 0] * 24)}
+    rot = torch.randn(B * 24, 1, 1, 128, generator=g)
+    gpara = torch.randn(B, 1, 1, 13, generator=g)
+    p_ref = torch.empty(B, 1, 1, 229); ref.gcn_head(gp, rot, gpara, p_ref)
+    gpc = {k: ([t.to(DEV) for t in v] if isinstance(v, list) else v.to(DEV)) for k, v in gp.items()}
+    p = torch.empty(B, 1, 1, 229, device=DEV); ops.gcn_head(gpc, rot.to(DEV), gpara.to(DEV), p)
+    assert (p.cpu() - p_ref).abs().max() < 5e-5

@@ -1,0 +1,82 @@
+"""CPU tests of the host logic of the network half (graph wiring, BatchNorm folding, weight packing,
+buffer planning, state_dict surface) using the torch test double of the kernel-level ops
+(tests/emul_ops.py) against golden vectors produced by the reference's own modules."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from emul_ops import TorchEmulOps
+from net_common import GOLD, build, check_against_golden, make_image
+
+
+def test_state_dict_surface_matches_reference():
+    """Every key / shape of the reference's img2iuv + smpl_para_Outs state_dict exists here (W48)."""
+    import danet_b200
+    from danet_b200 import synthetic
+    net = danet_b200.DaNet(None, synthetic.make_mean_params(0), pretrained=False, width=48,
+                           smpl_model=synthetic.make_smpl_model(0), dp_mesh=synthetic.make_dp_mesh(0))
+    mine = {k: tuple(v.shape) for k, v in net.state_dict().items() if not k.startswith("iuv2smpl.smpl.")}
+    ref = {}
+    for line in open(os.path.join(GOLD, "state_dict_keys_w48.txt")):
+        k, shp = line.split()
+        ref[k] = () if shp == "scalar" else tuple(int(d) for d in shp.split("x"))
+    assert set(ref) == set(mine), (sorted(set(ref) - set(mine))[:5], sorted(set(mine) - set(ref))[:5])
+    for k in ref:
+        assert ref[k] == mine[k], (k, ref[k], mine[k])
+    assert any(k.startswith("iuv2smpl.smpl.") for k in net.state_dict())
+    assert net.img2iuv.dp2smpl_mapping[7] == [8, 10, 12, 14, 5, 5]
+    assert hasattr(net, "iuv_renderer") and hasattr(net.iuv2smpl, "smpl")
+
+
+@pytest.mark.parametrize("width", [32, 48])
+def test_plan_with_emulated_kernels_matches_reference_golden(width):
+    net = build(width, ops=TorchEmulOps())
+    out = net.infer_net(make_image(2, 100))
+    assert out["para"].shape == (2, 229)
+    assert out["visualization"]["part_iuv_pred"].shape == (2, 24, 3, 7, 56, 56)
+    check_against_golden(out, width, para_tol=5e-5, kps_tol=5e-5, margin_eps=1e-3)
+    # rotation block of para is orthonormal (rot6d_to_rotmat)
+    R = out["para"][:, 13:].reshape(-1, 3, 3)
+    assert (R @ R.transpose(1, 2) - torch.eye(3)).abs().max() < 1e-5
+
+
+def test_infer_net_requires_eval_mode_and_cuda():
+    net = build(32, ops=TorchEmulOps())
+    net.train()
+    with pytest.raises(ValueError):
+        net.infer_net(make_image(1, 1))
+    net.eval()
+    net._test_ops = None
+    with pytest.raises(RuntimeError):                 # no CPU fallback in the product path
+        net.infer_net(make_image(1, 1))
+    with pytest.raises(NotImplementedError):
+        net({"img": None})
+
+
+def test_buffer_plan_reuses_memory_without_aliasing_live_tensors():
+    net = build(32, ops=TorchEmulOps())
+    plan = net.plan_for(1, "cpu", ops=TorchEmulOps())
+    g = plan.g
+    total = sum(t.nmult * t.H * t.W * t.Cp * 4 for t in g.tensors.values() if t.dtype == "f32")
+    assert plan.bytes_alloc < 0.5 * total               # liveness-based reuse is effective
+    # an op never reads and writes the same storage
+    for op in g.ops:
+        y = op.get("y")
+        if y is None:
+            continue
+        ins = [op.get(k) for k in ("x", "res", "hm", "gpara")] + [t for t, _ in op.get("terms", [])]
+        for t in ins:
+            if t is not None and t.dtype == "f32" and y.dtype == "f32":
+                assert plan.buf[t.name].data_ptr() != plan.buf[y.name].data_ptr(), (op["op"], t, y)
+
+
+def test_pretrained_flag_needs_files():
+    import danet_b200
+    from danet_b200 import synthetic
+    with pytest.raises(ValueError):
+        danet_b200.DaNet(None, synthetic.make_mean_params(0), pretrained=True, width=48,
+                         smpl_model=synthetic.make_smpl_model(0), dp_mesh=synthetic.make_dp_mesh(0))
+    with pytest.raises(ValueError):
+        danet_b200.DaNet(None, "/nonexistent/smpl_mean_params.npz", pretrained=False)

@@ -1,0 +1,29 @@
+"""Times the fused SMPL kernel over batch sizes / body blockings (CUDA events). Dev tool."""
+import sys, os, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import danet_b200
+from oracle import synth
+
+dev = torch.device("cuda:0")
+model = synth.make_smpl_model(0)
+smpl = danet_b200.SMPL(model).to(dev)
+res = []
+for B in (64, 512, 4096, 8192):
+    betas = torch.randn(B, 10, device=dev)
+    x6 = torch.randn(B, 24, 6, device=dev)
+    for nb in (4, 8, 16):
+        for _ in range(3):
+            smpl(betas=betas, pose6d=x6, bodies_per_cta=nb)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 10
+        e0.record()
+        for _ in range(n):
+            smpl(betas=betas, pose6d=x6, bodies_per_cta=nb)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        res.append({"B": B, "nb": nb, "ms": ms, "bodies_per_s": B / ms * 1e3, "verts_per_s": B * 6890 / ms * 1e3})
+        print(res[-1], flush=True)
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(res, open("gpurun_out/lbs_sweep.json", "w"), indent=1)

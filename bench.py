@@ -1,0 +1,391 @@
+"""Benchmark of the DaNet inference hot path (BASELINE.json metric: images/sec, DaNet forward
+bs=64 224x224, HRNet-W48 + SMPL + IUV_Renderer; plus SMPL LBS vertices/sec and roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+N > 1 is launched by torchrun (one rank per GPU, NCCL); batches are sharded image-parallel (weak
+scaling: 64 images per GPU) and the only collective is one all_gather of the outputs per step.
+Prints ONE JSON line on rank 0 (contract in the task statement)."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOP_PER_IMG = {48: 46.5e9, 32: 29.5e9}            # 2 x conv/linear MACs of a2+a3+a6
+LBS_BYTES_PER_BODY = 84460.0                        # SURVEY section 8d compulsory HBM bytes / body
+LBS_FLOP_PER_BODY = 15.8e6
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"],
+                    bf16_tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = []
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                out["sm_max_mhz"] = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active") and name not in out["reasons"]:
+                        out["reasons"].append(name)
+            except Exception:
+                continue
+        if sm:
+            sm.sort()
+            out["sm_mhz"] = sm[len(sm) // 2]
+            out["samples"] = len(sm)
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arms (reference's own modules when /root/reference exists, else the oracle port)
+# ---------------------------------------------------------------------------------------------
+def cpu_step_factory(width, B, seed=0):
+    """Returns (step_fn, kind, description).  One step = B images through the CPU implementation of
+    the same path: network half + SMPL LBS + IUV rasteriser."""
+    import numpy as np
+    import torch
+    from danet_b200 import synthetic
+    from oracle import lbs as olbs, raster as oraster, ref_import
+    torch.set_num_threads(os.cpu_count())
+    model, mesh = synthetic.make_smpl_model(seed), synthetic.make_dp_mesh(seed)
+    tex = synthetic.dp_textures(mesh)
+    g = torch.Generator().manual_seed(0)
+    img = torch.randn(B, 3, 224, 224, generator=g)
+    if ref_import.available():
+        import contextlib
+        from oracle import gen_golden_net
+        with contextlib.redirect_stdout(sys.stderr):          # the reference prints banners on import
+            ns = ref_import.load(width)
+            est, pred, _ = gen_golden_net.build_reference(ns, width, seed)
+        kind = "reference"
+        desc = "reference modules (IUV_Estimator + iuvmap_clean + DecomposedPredictor) imported from /root/reference"
+
+        def net(x):
+            return ref_import.infer_para(ns, est, pred, x)["para"]
+    else:
+        import danet_b200
+        from oracle.net_ops import TorchEmulOps
+        m = danet_b200.DaNet(None, synthetic.make_mean_params(seed), pretrained=False, width=width,
+                             smpl_model=model, dp_mesh=mesh)
+        m.load_state_dict(synthetic.keyed_state_dict(m.state_dict(), seed))
+        m.eval()
+        m._test_ops = TorchEmulOps()
+        kind = "port"
+        desc = "oracle port: the same graph through torch CPU ops (oracle/net_ops.py)"
+
+        def net(x):
+            return m.infer_net(x)["para"]
+
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(max_workers=min(B, os.cpu_count()))
+    oraster.build()
+
+    def step():
+        para = net(img).numpy()
+        R = para[:, 13:].reshape(B, 24, 3, 3)
+        out = olbs.smpl_forward(model, para[:, 3:13], R[:, 1:], R[:, :1], pose2rot=False, dtype=np.float32)
+        verts, cam = out["vertices"].astype(np.float32), para[:, :3].copy()
+        # the C rasteriser is single-threaded per call; ctypes drops the GIL, so images run in parallel
+        list(pool.map(lambda b: oraster.verts2uvimg(verts[b:b + 1], cam[b:b + 1], mesh, tex), range(B)))
+        return B
+
+    return step, kind, desc + " + oracle/lbs.py (numpy fp32) + oracle/raster.c"
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = args.cpu_batch
+    step, kind, desc = cpu_step_factory(args.width, B)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    n = 0
+    for _ in range(args.steps):
+        n += step()
+    dt = time.perf_counter() - t0
+    val = n / dt
+    cores = os.cpu_count()
+    sample = "%d steps x %d images, W%d, %s" % (args.steps, B, args.width, desc)
+    line = {"impl": "reference", "metric": "images/sec DaNet fwd (HRNet-W%d + part regressors + SMPL LBS + IUV render)" % args.width,
+            "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[2]: DaNet forward batch=64 synthetic 224x224, HRNet-W%d + IUV_Renderer" % args.width,
+                       "cpu_step_batch": B},
+            "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    import danet_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("bench.py --gpus %d must be launched with torchrun (one rank per GPU)" % args.gpus)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, W = args.batch, args.width
+    net = danet_b200.build_synthetic_danet(width=W, seed=0, device=dev, conv_algo=args.conv,
+                                           use_cuda_graph=not args.no_graph)
+    smpl, rend = net.iuv2smpl.smpl, net.iuv_renderer
+    nrot = 4                                          # 4 x 38.5 MB input batches > 126 MB L2
+    g = torch.Generator().manual_seed(1234 + rank)
+    host_in = [torch.randn(B, 3, 224, 224, generator=g).pin_memory() for _ in range(nrot)]
+    dev_in = [t.to(dev) for t in host_in]
+    gathered = torch.empty(world * B, 229, device=dev) if world > 1 else None
+
+    def hot_path(x):
+        para = net.infer_net(x)["para"]
+        R = para[:, 13:].reshape(B, 24, 3, 3)
+        out = smpl(betas=para[:, 3:13].contiguous(), body_pose=R[:, 1:], global_orient=R[:, :1], pose2rot=False)
+        img = rend.verts2uvimg(out.vertices, para[:, :3].contiguous())
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, para)      # the single NCCL gather of outputs
+        return para, img
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        hot_path(dev_in[i % nrot])
+    sync()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    e0.record()
+    for i in range(args.steps):
+        hot_path(dev_in[i % nrot])
+    e1.record()
+    sync()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- end-to-end through the public API with host buffers (H2D + D2H inside the timed region) ----
+    host_para = torch.empty(B, 229).pin_memory()
+    host_img = torch.empty(B, 3, 56, 56).pin_memory()
+
+    def e2e_step(i):
+        x = host_in[i % nrot].to(dev, non_blocking=True)
+        para, img = hot_path(x)
+        host_para.copy_(para, non_blocking=True)
+        host_img.copy_(img, non_blocking=True)
+
+    for i in range(3):
+        e2e_step(i)
+    sync()
+    e0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    e1.record()
+    sync()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / (float(t.item()) * 1e-3)
+
+    plan = net.plan_for(B, dev)
+    launches_per_step = plan.n_launch + 3 + 4 + (1 if world > 1 else 0)
+    line = None
+    if rank == 0:
+        pk = peaks()
+        # ---- per-kernel-class timing of one profiled step (CUDA events on the launch stream) ----
+        prof = profile_step(net, plan, dev_in[0], dev)
+        conv_ms = prof["conv_ms"]
+        flops = FLOP_PER_IMG.get(W, 0.0) * B
+        conv_tflops = flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        tf32_peak = pk["bf16_tflops_sustained"] / 2.0
+        roof = {"bound": "tensor", "kernel": prof["conv_kernel"], "achieved": conv_tflops, "peak": tf32_peak,
+                "unit": "TFLOP/s", "frac": conv_tflops / tf32_peak if tf32_peak else None, "traffic": None,
+                "peak_note": "TF32 dense = half of the %s bf16 sustained cuBLAS figure (%.0f TFLOP/s); fp32-FMA "
+                             "launches are rated against the same denominator" % (pk["source"], pk["bf16_tflops_sustained"]),
+                "algorithmic_flop_per_launch_group": flops, "conv_ms_per_step": conv_ms,
+                "conv_share_of_step": conv_ms / (ms / args.steps), "n_conv_tc": plan.n_tc,
+                "n_conv_total": prof["n_conv"], "other_ms": prof["other_ms"]}
+        lbs = lbs_bench(smpl, dev, pk)
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            cpu = cpu_baseline(W, args.cpu_batch)
+        line = {"metric": "images/sec DaNet fwd bs=%d 224x224 (HRNet-W%d + part regressors + SMPL LBS + IUV render)" % (B, W),
+                "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "tf32" if plan.n_tc else "f32", "data": "synthetic",
+                "config": {"workload": "configs[2]: DaNet forward batch=64 synthetic 224x224, HRNet-W%d + IUV_Renderer" % W,
+                           "per_gpu_batch": B, "global_batch": B * world, "parallelism": "image-sharded x%d, one all_gather of para" % world,
+                           "conv_path": "tcgen05 TF32 (%d of %d convs) + fp32 FMA" % (plan.n_tc, prof["n_conv"]),
+                           "cuda_graph": not args.no_graph,
+                           "l2": "inputs rotate over %d batches (%.0f MB > 126 MB L2); activations (%.1f GB/step) exceed L2"
+                                 % (nrot, nrot * B * 3 * 224 * 224 * 4 / 1e6, plan.bytes_alloc / 1e9),
+                           "weights": "deterministic keyed random init of the reference architecture (synthetic.keyed_state_dict)"},
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * 224 * 224 * 4,
+                        "d2h_bytes_per_step": B * 229 * 4 + B * 3 * 56 * 56 * 4},
+                "gpu_launches": launches_per_step * args.steps,
+                "roofline": roof, "lbs": lbs, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+def profile_step(net, plan, x, dev):
+    """One eager (non-graph) step with CUDA events around every launch; groups by kernel class."""
+    import torch
+    saved = plan.use_cuda_graph
+    plan.use_cuda_graph = False
+    ops = plan.ops
+    events = []
+
+    class Timed(object):
+        def __getattr__(self, name):
+            fn = getattr(ops, name)
+            if name.startswith("conv_tc") or not callable(fn):
+                return fn
+
+            def wrapped(*a, **k):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                r = fn(*a, **k)
+                e1.record()
+                tag = name
+                if name == "conv2d":
+                    tag = "conv_tc" if a[1] == 1 else "conv_simt"
+                events.append((tag, e0, e1))
+                return r
+            return wrapped
+    plan.ops = Timed()
+    plan.run(x)
+    torch.cuda.synchronize()
+    plan.ops = ops
+    plan.use_cuda_graph = saved
+    agg = {}
+    for tag, e0, e1 in events:
+        agg[tag] = agg.get(tag, 0.0) + e0.elapsed_time(e1)
+    conv_ms = agg.get("conv_tc", 0.0) + agg.get("conv_simt", 0.0)
+    n_conv = sum(1 for t, _, _ in events if t.startswith("conv"))
+    kern = "k_conv_tc (tcgen05 TF32) + k_conv_simt" if agg.get("conv_tc") else "k_conv_simt (fp32 FMA implicit GEMM)"
+    return {"conv_ms": conv_ms, "n_conv": n_conv, "conv_kernel": kern,
+            "other_ms": {k: v for k, v in agg.items() if not k.startswith("conv")},
+            "conv_tc_ms": agg.get("conv_tc", 0.0), "conv_simt_ms": agg.get("conv_simt", 0.0)}
+
+
+def lbs_bench(smpl, dev, pk, B=8192):
+    """SMPL LBS vertices/sec on a batch whose output (B*82.7 KB = 677 MB) exceeds L2."""
+    import torch
+    betas = torch.randn(B, 10, device=dev)
+    x6 = torch.randn(B, 24, 6, device=dev)
+    for _ in range(3):
+        smpl(betas=betas, pose6d=x6)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 10
+    e0.record()
+    for _ in range(n):
+        smpl(betas=betas, pose6d=x6)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    bodies = B / (ms * 1e-3)
+    gbs = bodies * LBS_BYTES_PER_BODY / 1e9
+    return {"metric": "SMPL LBS vertices/sec (forward incl. 49 joints)", "value": bodies * 6890, "unit": "vertices/s",
+            "batch": B, "ms": ms, "bodies_per_s": bodies,
+            "roofline_hbm": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+                             "algorithmic_bytes_per_body": LBS_BYTES_PER_BODY},
+            "roofline_fma": {"achieved_tflops": bodies * LBS_FLOP_PER_BODY / 1e12, "nominal_fp32_tflops": 80.0,
+                             "note": "dense pose-corrective contraction (4.28 MMAC/body) makes the fused kernel FMA-bound (SURVEY 8d)"}}
+
+
+def cpu_baseline(width, B):
+    step, kind, desc = cpu_step_factory(width, B)
+    step()
+    t0 = time.perf_counter()
+    n, it = 0, 0
+    while it < 2 or (time.perf_counter() - t0 < 10.0 and it < 20):
+        n += step()
+        it += 1
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "images/s", "cores": os.cpu_count(), "kind": kind,
+            "sample": "%d steps x %d images (%.1f s), W%d; %s" % (it, B, dt, width, desc)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--width", type=int, default=48)
+    ap.add_argument("--conv", default="auto", choices=["auto", "tc", "simt"])
+    ap.add_argument("--cpu-batch", type=int, default=8)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,4 +1,7 @@
-"""Torch (CPU) emulation of the kernel-level ops behind plan.CudaOps -- a TEST DOUBLE used only to
+"""Torch (CPU) restatement of the kernel-level ops behind plan.CudaOps -- TEST INFRASTRUCTURE
+(oracle/__init__.py): the checker of the network-half kernels, the test double that lets the host
+logic run without a GPU, and (driven through the same graph) the CPU port timed by bench.py's
+cpu_baseline / --impl reference legs when /root/reference is absent.  Used only to
 check the host logic (graph wiring, BN folding, weight packing, buffer planning) on machines
 without a GPU.  Each method restates the semantics documented in include/danet_b200.h with plain
 torch ops; it is never used by the package itself."""

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from emul_ops import TorchEmulOps
+from oracle.net_ops import TorchEmulOps
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from emul_ops import TorchEmulOps
+from oracle.net_ops import TorchEmulOps
 from net_common import GOLD, build, check_against_golden, make_image
 
 

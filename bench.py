@@ -23,6 +23,16 @@ LBS_BYTES_PER_BODY = 84460.0                        # SURVEY section 8d compulso
 LBS_FLOP_PER_BODY = 15.8e6
 
 
+def host_threads():
+    """Threads for the CPU arms: the cores this process may run on, capped at 32 (oneDNN on small
+    batches degrades badly when a 128-core box is oversubscribed)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(1, min(n, int(os.environ.get("DANET_CPU_THREADS", "32"))))
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -83,7 +93,7 @@ def cpu_step_factory(width, B, seed=0):
     import torch
     from danet_b200 import synthetic
     from oracle import lbs as olbs, raster as oraster, ref_import
-    torch.set_num_threads(os.cpu_count())
+    torch.set_num_threads(host_threads())
     model, mesh = synthetic.make_smpl_model(seed), synthetic.make_dp_mesh(seed)
     tex = synthetic.dp_textures(mesh)
     g = torch.Generator().manual_seed(0)
@@ -114,7 +124,7 @@ def cpu_step_factory(width, B, seed=0):
             return m.infer_net(x)["para"]
 
     from concurrent.futures import ThreadPoolExecutor
-    pool = ThreadPoolExecutor(max_workers=min(B, os.cpu_count()))
+    pool = ThreadPoolExecutor(max_workers=min(B, host_threads()))
     oraster.build()
 
     def step():
@@ -143,7 +153,7 @@ def run_reference_arm(args):
         n += step()
     dt = time.perf_counter() - t0
     val = n / dt
-    cores = os.cpu_count()
+    cores = host_threads()
     sample = "%d steps x %d images, W%d, %s" % (args.steps, B, args.width, desc)
     line = {"impl": "reference", "metric": "images/sec DaNet fwd (HRNet-W%d + part regressors + SMPL LBS + IUV render)" % args.width,
             "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -357,14 +367,16 @@ def lbs_bench(smpl, dev, pk, B=8192):
 
 def cpu_baseline(width, B):
     step, kind, desc = cpu_step_factory(width, B)
-    step()
+    t0 = time.perf_counter()
+    step()                                            # warm-up (also bounds the sample: see below)
+    warm = time.perf_counter() - t0
     t0 = time.perf_counter()
     n, it = 0, 0
-    while it < 2 or (time.perf_counter() - t0 < 10.0 and it < 20):
+    while it < 1 or (time.perf_counter() - t0 + warm < 20.0 and it < 20):
         n += step()
         it += 1
     dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": "images/s", "cores": os.cpu_count(), "kind": kind,
+    return {"value": n / dt, "unit": "images/s", "cores": host_threads(), "kind": kind,
             "sample": "%d steps x %d images (%.1f s), W%d; %s" % (it, B, dt, width, desc)}
 
 
@@ -377,7 +389,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--width", type=int, default=48)
     ap.add_argument("--conv", default="auto", choices=["auto", "tc", "simt"])
-    ap.add_argument("--cpu-batch", type=int, default=8)
+    ap.add_argument("--cpu-batch", type=int, default=4)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

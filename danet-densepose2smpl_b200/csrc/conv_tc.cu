@@ -1,17 +1,414 @@
-// tcgen05 TF32 implicit-GEMM convolution (sm_100a).  Placeholder until the kernel lands: reports
-// "unsupported" for every shape so callers route through the fp32 FMA path.
+// tcgen05 TF32 implicit-GEMM convolution for sm_100a (stride-1 1x1 / 3x3, NHWC fp32 activations).
+// The fast path of models/module/hr_module.py + res_module.py convolutions (conv + folded BN +
+// residual + ReLU); everything it does not take goes through csrc/conv_simt.cu.
+//
+// Design (one persistent CTA per SM, warp-specialised, no tensor maps):
+//   M tile  = 128 output pixels = 16 rows x 8 columns of one image; N tile = up to 256 output
+//             channels; accumulators live in TMEM (double-buffered, 2 x N columns of 512).
+//   A (activations): the (16+k-1) x (8+k-1) input HALO of the tile is loaded ONCE per channel
+//             chunk by 4 producer warps (coalesced 16-byte global loads, TF32 rounding, 16-byte
+//             st.shared) into the canonical no-swizzle K-major UMMA layout
+//                 [channel group of 4][halo pixel][4 floats]
+//             where 8 consecutive MMA rows are 8 consecutive pixels of one halo row (core matrix =
+//             8 x 16 B contiguous), SBO = halo row pitch, LBO = channel-group plane pitch.  All
+//             k*k filter taps are then just different START ADDRESSES of the same smem tile, so each
+//             input element crosses L2->SM about (18*10)/(16*8) = 1.4x instead of 9x.
+//   B (weights): pre-packed once (danet_conv_tc_pack) into the exact smem image of every
+//             (N tile, channel chunk, tap, sub-chunk) block, streamed by 1-D cp.async.bulk copies
+//             that complete on an mbarrier (no cuTensorMap needed).
+//   MMA     : one elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N, K=8) and
+//             releases smem stages / publishes accumulators with tcgen05.commit -> mbarrier.
+//   Epilogue: 4 warps read TMEM with tcgen05.ld (32 lanes x 16 columns), add bias (+ residual),
+//             ReLU, and store 16-byte vectors to NHWC global memory.
+// Every mbarrier wait is bounded (traps instead of hanging the device).
 #include "common.cuh"
 
 namespace danet {
-int conv_tc_launch(const danet_conv_desc*, const float*, const void*, const float*, const float*, float*, cudaStream_t) {
-    set_error("conv_tc_launch: tcgen05 path not built");
-    return -1;
+namespace tc {
+
+constexpr int kTileH = 16, kTileW = 8;
+constexpr int kThreads = 320;            // warp0: B producer, warp1: MMA + TMEM alloc, warps 2-5: A producers, warps 6-9: epilogue
+constexpr int kNumProducers = 128;
+constexpr int kMaxBStages = 8;
+constexpr int kSmemBudget = 200 * 1024;
+
+struct Geom {
+    int N, H, W, Cin, Cout, ks, pad, relu, wsets;
+    int Wh, Hh, npx, plane_bytes;
+    int AC, BC, nchunks, nbsub, cgA;     // cgA = AC/4
+    int NT, ntn;
+    int tiles_w, tiles_h, total_tiles;
+    int a_stage_bytes, b_stage_bytes, nb_stages;
+    int smem_bytes;
+    long long blocks_per_set;            // packed weight blocks per weight set
+};
+
+static bool make_geom(const danet_conv_desc* d, Geom* g) {
+    if (d->stride != 1 || !(d->ksize == 1 || d->ksize == 3) || d->pad != d->ksize / 2) return false;
+    if (d->Cin % 8 != 0 || d->Cout % 4 != 0 || d->H < 7 || d->W < 7) return false;
+    g->N = d->N; g->H = d->H; g->W = d->W; g->Cin = d->Cin; g->Cout = d->Cout; g->ks = d->ksize;
+    g->pad = d->pad; g->relu = d->relu; g->wsets = d->wsets;
+    int ac = 0;
+    for (int c = 64; c >= 8; c -= 8) if (d->Cin % c == 0) { ac = c; break; }
+    if (ac == 0) return false;
+    g->AC = ac; g->cgA = ac / 4; g->nchunks = d->Cin / ac;
+    int bc = 0;
+    for (int c = 32; c >= 8; c -= 8) if (ac % c == 0) { bc = c; break; }
+    g->BC = bc; g->nbsub = ac / bc;
+    const int np = (d->Cout + 15) / 16 * 16;
+    g->ntn = (np + 255) / 256;
+    g->NT = ((np + g->ntn - 1) / g->ntn + 15) / 16 * 16;
+    g->Wh = kTileW + d->ksize - 1; g->Hh = kTileH + d->ksize - 1; g->npx = g->Wh * g->Hh;
+    g->plane_bytes = (g->npx | 1) * 16;                      // odd number of 16-byte units: conflict-free producer stores
+    g->a_stage_bytes = (g->plane_bytes * g->cgA + 127) / 128 * 128;
+    g->b_stage_bytes = g->BC * g->NT * 4;
+    int nb = (kSmemBudget - 2 * g->a_stage_bytes) / g->b_stage_bytes;
+    if (nb < 2) return false;
+    g->nb_stages = nb > kMaxBStages ? kMaxBStages : nb;
+    g->tiles_w = (d->W + kTileW - 1) / kTileW; g->tiles_h = (d->H + kTileH - 1) / kTileH;
+    g->total_tiles = d->N * g->tiles_h * g->tiles_w * g->ntn;
+    g->smem_bytes = 2 * g->a_stage_bytes + g->nb_stages * g->b_stage_bytes + 256 + 1024;
+    if (g->smem_bytes < 120 * 1024) g->smem_bytes = 120 * 1024;      // one CTA per SM: each CTA allocates all 512 TMEM columns
+    g->blocks_per_set = (long long)g->ntn * g->nchunks * d->ksize * d->ksize * g->nbsub;
+    return true;
 }
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t it = 0; it < (1u << 26); ++it) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();                                        // bounded wait: never hang the device
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+    const uint32_t hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+struct Args {
+    Geom g;
+    const float* x; const float* wpk; const float* bias; const float* res; float* y;
+};
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+k_conv_tc(const Args a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const Geom& g = a.g;
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t sA = sbase;
+    const uint32_t sB = sbase + 2 * g.a_stage_bytes;
+    const uint32_t sBar = sB + g.nb_stages * g.b_stage_bytes;
+    // barrier map (8 bytes each)
+    const uint32_t bar_a_full = sBar, bar_a_empty = sBar + 16, bar_acc_full = sBar + 32, bar_acc_empty = sBar + 48;
+    const uint32_t bar_b_full = sBar + 64, bar_b_empty = sBar + 64 + 8 * kMaxBStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (sBar - sbase) + 64 + 16 * kMaxBStages);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar_a_full + 8 * i, kNumProducers);
+            mbar_init(bar_a_empty + 8 * i, 1);
+            mbar_init(bar_acc_full + 8 * i, 1);
+            mbar_init(bar_acc_empty + 8 * i, 128);
+        }
+        for (int i = 0; i < g.nb_stages; ++i) { mbar_init(bar_b_full + 8 * i, 1); mbar_init(bar_b_empty + 8 * i, 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int taps = g.ks * g.ks;
+    const int HWC = g.H * g.W;
+
+    if (warp == 0) {
+        // ================= B producer: bulk copies of pre-packed weight blocks =================
+        if (lane == 0) {
+            int bs = 0; uint32_t bph = 0;
+            for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+                const int nt = tile % g.ntn;
+                const int img = tile / (g.ntn * g.tiles_w * g.tiles_h);
+                const int ws = img % g.wsets;
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wpk) +
+                    ((long long)ws * g.blocks_per_set + (long long)nt * g.nchunks * taps * g.nbsub) * g.b_stage_bytes;
+                const int nblk = g.nchunks * taps * g.nbsub;
+                for (int b = 0; b < nblk; ++b) {
+                    mbar_wait(bar_b_empty + 8 * bs, bph ^ 1);
+                    mbar_expect_tx(bar_b_full + 8 * bs, g.b_stage_bytes);
+                    bulk_g2s(sB + bs * g.b_stage_bytes, src + (long long)b * g.b_stage_bytes, g.b_stage_bytes, bar_b_full + 8 * bs);
+                    if (++bs == g.nb_stages) { bs = 0; bph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.NT >> 3) << 17) | ((128u >> 4) << 24);
+            int as = 0, bs = 0, cs = 0; uint32_t aph = 0, bph = 0, cph = 0;
+            const uint32_t sbo_a = g.Wh * 16, lbo_a = g.plane_bytes;
+            const uint32_t sbo_b = 128, lbo_b = g.NT * 16;
+            for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+                mbar_wait(bar_acc_empty + 8 * cs, cph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + cs * g.NT;
+                uint32_t acc = 0;
+                for (int c = 0; c < g.nchunks; ++c) {
+                    mbar_wait(bar_a_full + 8 * as, aph);
+                    tc_fence_after();
+                    const uint32_t a_st = sA + as * g.a_stage_bytes;
+                    for (int t = 0; t < taps; ++t) {
+                        const uint32_t tap_off = ((t / g.ks) * g.Wh + (t % g.ks)) * 16;
+                        for (int s = 0; s < g.nbsub; ++s) {
+                            mbar_wait(bar_b_full + 8 * bs, bph);
+                            tc_fence_after();
+                            const uint32_t b_st = sB + bs * g.b_stage_bytes;
+                            for (int j = 0; j < g.BC / 8; ++j) {
+                                const uint64_t ad = make_desc(a_st + (s * (g.BC / 4) + 2 * j) * g.plane_bytes + tap_off, lbo_a, sbo_a);
+                                const uint64_t bd = make_desc(b_st + (2 * j) * lbo_b, lbo_b, sbo_b);
+                                tc_mma_tf32(d_tmem, ad, bd, idesc, acc);
+                                acc = 1;
+                            }
+                            tc_commit(bar_b_empty + 8 * bs);
+                            if (++bs == g.nb_stages) { bs = 0; bph ^= 1; }
+                        }
+                    }
+                    tc_commit(bar_a_empty + 8 * as);
+                    if (++as == 2) { as = 0; aph ^= 1; }
+                }
+                tc_commit(bar_acc_full + 8 * cs);
+                if (++cs == 2) { cs = 0; cph ^= 1; }
+            }
+        }
+    } else if (warp < 6) {
+        // ================= A producers: halo tile -> smem (no-swizzle K-major) =================
+        const int pt = threadIdx.x - 64;                        // 0..127
+        const int items = g.npx * g.cgA;
+        int as = 0; uint32_t aph = 0;
+        for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+            int r = tile / g.ntn;
+            const int tw = r % g.tiles_w; r /= g.tiles_w;
+            const int th = r % g.tiles_h;
+            const int img = r / g.tiles_h;
+            const int h0 = th * kTileH - g.pad, w0 = tw * kTileW - g.pad;
+            const float* xi = a.x + (size_t)img * HWC * g.Cin;
+            for (int c = 0; c < g.nchunks; ++c) {
+                mbar_wait(bar_a_empty + 8 * as, aph ^ 1);
+                const uint32_t a_st = sA + as * g.a_stage_bytes;
+                const float* xc = xi + c * g.AC;
+                for (int it0 = pt; it0 < items; it0 += kNumProducers * 4) {
+                    float4 v[4];
+                    uint32_t dst[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int it = it0 + u * kNumProducers;
+                        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        dst[u] = 0xFFFFFFFFu;
+                        if (it < items) {
+                            const int px = it / g.cgA, cg = it - px * g.cgA;
+                            const int hh = px / g.Wh, ww = px - hh * g.Wh;
+                            const int ih = h0 + hh, iw = w0 + ww;
+                            dst[u] = a_st + cg * g.plane_bytes + px * 16;
+                            if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W)
+                                v[u] = __ldg(reinterpret_cast<const float4*>(xc + ((size_t)ih * g.W + iw) * g.Cin + cg * 4));
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (dst[u] != 0xFFFFFFFFu)
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst[u]), "f"(to_tf32(v[u].x)),
+                                         "f"(to_tf32(v[u].y)), "f"(to_tf32(v[u].z)), "f"(to_tf32(v[u].w)) : "memory");
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive(bar_a_full + 8 * as);
+                if (++as == 2) { as = 0; aph ^= 1; }
+            }
+        }
+    } else {
+        // ================= epilogue: TMEM -> bias/residual/ReLU -> global =================
+        const int q = warp & 3;                                  // TMEM lane quarter this warp may access
+        const int m = q * 32 + lane;
+        const int hh = m >> 3, ww = m & 7;
+        int cs = 0; uint32_t cph = 0;
+        for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+            const int nt = tile % g.ntn;
+            int r = tile / g.ntn;
+            const int tw = r % g.tiles_w; r /= g.tiles_w;
+            const int th = r % g.tiles_h;
+            const int img = r / g.tiles_h;
+            const int oh = th * kTileH + hh, ow = tw * kTileW + ww;
+            const bool valid = oh < g.H && ow < g.W;
+            const size_t pix = ((size_t)img * HWC + (size_t)oh * g.W + ow) * g.Cout;
+            const float* bias = a.bias ? a.bias + (size_t)(img % g.wsets) * g.Cout : nullptr;
+            mbar_wait(bar_acc_full + 8 * cs, cph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cs * g.NT;
+            for (int c0 = 0; c0 < g.NT; c0 += 16) {
+                float v[16];
+                tc_ld16(taddr + c0, v);
+                const int ch0 = nt * g.NT + c0;
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int ch = ch0 + 4 * j;
+                        if (ch < g.Cout) {
+                            float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            if (bias) {
+                                const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + ch));
+                                o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+                            }
+                            if (a.res) {
+                                const float4 rr = __ldg(reinterpret_cast<const float4*>(a.res + pix + ch));
+                                o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+                            }
+                            if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                            *reinterpret_cast<float4*>(a.y + pix + ch) = o;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(bar_acc_empty + 8 * cs);
+            if (++cs == 2) { cs = 0; cph ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+// weight packing: SIMT layout [wsets][ks*ks*Cin][Cout] -> smem-image blocks, TF32-rounded
+__global__ void k_pack(const Geom g, const float* __restrict__ w, float* __restrict__ out) {
+    const long long total = (long long)g.wsets * g.blocks_per_set * g.BC * g.NT;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int taps = g.ks * g.ks;
+    const int per_block = g.BC * g.NT;
+    long long blk = i / per_block;
+    int e = (int)(i % per_block);
+    const int j = e & 3; e >>= 2;
+    const int n = e % g.NT;
+    const int kg = e / g.NT;
+    const int s = (int)(blk % g.nbsub); blk /= g.nbsub;
+    const int t = (int)(blk % taps); blk /= taps;
+    const int c = (int)(blk % g.nchunks); blk /= g.nchunks;
+    const int nt = (int)(blk % g.ntn);
+    const int ws = (int)(blk / g.ntn);
+    const int cin = c * g.AC + s * g.BC + kg * 4 + j;
+    const int co = nt * g.NT + n;
+    float v = 0.f;
+    if (co < g.Cout) v = w[((size_t)ws * taps * g.Cin + (size_t)t * g.Cin + cin) * g.Cout + co];
+    out[i] = to_tf32(v);
+}
+
+}  // namespace tc
+
+int conv_tc_launch(const danet_conv_desc* d, const float* x, const void* w_packed, const float* bias,
+                   const float* residual, float* y, cudaStream_t stream) {
+    tc::Args a;
+    if (!tc::make_geom(d, &a.g)) { set_error("conv_tc_launch: unsupported shape"); return -1; }
+    a.x = x; a.wpk = (const float*)w_packed; a.bias = bias; a.res = residual; a.y = y;
+    static int sm_count = 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        int dev = 0;
+        DANET_CUDA(cudaGetDevice(&dev));
+        DANET_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+        DANET_CUDA(cudaFuncSetAttribute(tc::k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    const int grid = a.g.total_tiles < sm_count ? a.g.total_tiles : sm_count;
+    tc::k_conv_tc<<<grid, tc::kThreads, a.g.smem_bytes, stream>>>(a);
+    DANET_LAUNCH_CHECK();
+    return 0;
+}
+
 }  // namespace danet
 
-extern "C" int danet_conv_tc_supported(const danet_conv_desc*) { return 0; }
-extern "C" int64_t danet_conv_tc_packed_bytes(const danet_conv_desc*) { return 0; }
-extern "C" int danet_conv_tc_pack(const danet_conv_desc*, const float*, void*, danet_stream_t) {
-    danet::set_error("danet_conv_tc_pack: tcgen05 path not built");
-    return -1;
+using namespace danet;
+
+extern "C" int danet_conv_tc_supported(const danet_conv_desc* d) {
+    tc::Geom g;
+    return d && tc::make_geom(d, &g) ? 1 : 0;
+}
+
+extern "C" int64_t danet_conv_tc_packed_bytes(const danet_conv_desc* d) {
+    tc::Geom g;
+    if (!d || !tc::make_geom(d, &g)) return 0;
+    return (int64_t)d->wsets * g.blocks_per_set * g.b_stage_bytes;
+}
+
+extern "C" int danet_conv_tc_pack(const danet_conv_desc* d, const float* w_simt, void* w_packed, danet_stream_t stream) {
+    tc::Geom g;
+    DANET_CHECK(d && tc::make_geom(d, &g), "danet_conv_tc_pack: shape not supported by the tcgen05 path");
+    DANET_CHECK(w_simt && w_packed, "danet_conv_tc_pack: null pointer");
+    const long long total = (long long)g.wsets * g.blocks_per_set * g.BC * g.NT;
+    tc::k_pack<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g, w_simt, (float*)w_packed);
+    DANET_LAUNCH_CHECK();
+    return 0;
 }

@@ -1,4 +1,4 @@
-// tcgen05 TF32 implicit-GEMM convolution for sm_100a (stride-1 1x1 / 3x3, NHWC fp32 activations).
+// tcgen05 TF32 implicit-GEMM convolution for sm_100a (1x1 / 3x3 / 7x7, stride 1 or 2, NHWC fp32).
 // The fast path of models/module/hr_module.py + res_module.py convolutions (conv + folded BN +
 // residual + ReLU); everything it does not take goes through csrc/conv_simt.cu.
 //
@@ -33,9 +33,11 @@ constexpr int kMaxBStages = 8;
 constexpr int kSmemBudget = 200 * 1024;
 
 struct Geom {
-    int N, H, W, Cin, Cout, ks, pad, relu, wsets;
-    int Wh, Hh, npx, plane_bytes;
+    int N, H, W, Cin, Cout, ks, pad, stride, relu, wsets;
+    int Ho, Wo;
+    int Wh, Hh, npx, Whh, parplane_units, plane_bytes;   // halo tile: Hh x Wh input pixels, stored column-parity split
     int AC, BC, nchunks, nbsub, cgA;     // cgA = AC/4
+    int TG, ntg;                         // filter taps per B stage, tap groups
     int NT, ntn;
     int tiles_w, tiles_h, total_tiles;
     int a_stage_bytes, b_stage_bytes, nb_stages;
@@ -44,12 +46,19 @@ struct Geom {
 };
 
 static bool make_geom(const danet_conv_desc* d, Geom* g) {
-    if (d->stride != 1 || !(d->ksize == 1 || d->ksize == 3) || d->pad != d->ksize / 2) return false;
-    if (d->Cin % 8 != 0 || d->Cout % 4 != 0 || d->H < 7 || d->W < 7) return false;
+    if (!(d->stride == 1 || d->stride == 2) || !(d->ksize == 1 || d->ksize == 3 || d->ksize == 7) || d->pad != d->ksize / 2) return false;
+    if (d->Cin % 8 != 0 || d->Cout % 4 != 0 || d->H < 4 || d->W < 4) return false;
     g->N = d->N; g->H = d->H; g->W = d->W; g->Cin = d->Cin; g->Cout = d->Cout; g->ks = d->ksize;
-    g->pad = d->pad; g->relu = d->relu; g->wsets = d->wsets;
+    g->pad = d->pad; g->stride = d->stride; g->relu = d->relu; g->wsets = d->wsets;
+    g->Ho = (d->H + 2 * d->pad - d->ksize) / d->stride + 1;
+    g->Wo = (d->W + 2 * d->pad - d->ksize) / d->stride + 1;
+    g->Wh = (kTileW - 1) * d->stride + d->ksize; g->Hh = (kTileH - 1) * d->stride + d->ksize; g->npx = g->Wh * g->Hh;
+    g->Whh = (g->Wh + d->stride - 1) / d->stride;
+    g->parplane_units = g->Hh * g->Whh;
+    g->plane_bytes = ((d->stride * g->parplane_units) | 1) * 16;   // odd number of 16-byte units: conflict-free producer stores
     int ac = 0;
-    for (int c = 64; c >= 8; c -= 8) if (d->Cin % c == 0) { ac = c; break; }
+    for (int c = 64; c >= 8; c -= 8)
+        if (d->Cin % c == 0 && g->plane_bytes * (c / 4) <= 50 * 1024) { ac = c; break; }
     if (ac == 0) return false;
     g->AC = ac; g->cgA = ac / 4; g->nchunks = d->Cin / ac;
     int bc = 0;
@@ -58,18 +67,21 @@ static bool make_geom(const danet_conv_desc* d, Geom* g) {
     const int np = (d->Cout + 15) / 16 * 16;
     g->ntn = (np + 255) / 256;
     g->NT = ((np + g->ntn - 1) / g->ntn + 15) / 16 * 16;
-    g->Wh = kTileW + d->ksize - 1; g->Hh = kTileH + d->ksize - 1; g->npx = g->Wh * g->Hh;
-    g->plane_bytes = (g->npx | 1) * 16;                      // odd number of 16-byte units: conflict-free producer stores
     g->a_stage_bytes = (g->plane_bytes * g->cgA + 127) / 128 * 128;
-    g->b_stage_bytes = g->BC * g->NT * 4;
+    const int taps = d->ksize * d->ksize;
+    const int tap_bytes = g->BC * g->NT * 4;
+    int tg = 1;
+    for (int t = taps; t >= 1; --t) if (taps % t == 0 && t * tap_bytes <= 32 * 1024) { tg = t; break; }
+    g->TG = tg; g->ntg = taps / tg;
+    g->b_stage_bytes = tg * tap_bytes;
     int nb = (kSmemBudget - 2 * g->a_stage_bytes) / g->b_stage_bytes;
     if (nb < 2) return false;
     g->nb_stages = nb > kMaxBStages ? kMaxBStages : nb;
-    g->tiles_w = (d->W + kTileW - 1) / kTileW; g->tiles_h = (d->H + kTileH - 1) / kTileH;
+    g->tiles_w = (g->Wo + kTileW - 1) / kTileW; g->tiles_h = (g->Ho + kTileH - 1) / kTileH;
     g->total_tiles = d->N * g->tiles_h * g->tiles_w * g->ntn;
     g->smem_bytes = 2 * g->a_stage_bytes + g->nb_stages * g->b_stage_bytes + 256 + 1024;
     if (g->smem_bytes < 120 * 1024) g->smem_bytes = 120 * 1024;      // one CTA per SM: each CTA allocates all 512 TMEM columns
-    g->blocks_per_set = (long long)g->ntn * g->nchunks * d->ksize * d->ksize * g->nbsub;
+    g->blocks_per_set = (long long)g->ntn * g->nchunks * g->ntg * g->nbsub;
     return true;
 }
 
@@ -89,7 +101,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
-    for (uint32_t it = 0; it < (1u << 26); ++it) {
+    for (uint32_t it = 0; it < (1u << 22); ++it) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -192,8 +204,8 @@ k_conv_tc(const Args a) {
                 const int img = tile / (g.ntn * g.tiles_w * g.tiles_h);
                 const int ws = img % g.wsets;
                 const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wpk) +
-                    ((long long)ws * g.blocks_per_set + (long long)nt * g.nchunks * taps * g.nbsub) * g.b_stage_bytes;
-                const int nblk = g.nchunks * taps * g.nbsub;
+                    ((long long)ws * g.blocks_per_set + (long long)nt * g.nchunks * g.ntg * g.nbsub) * g.b_stage_bytes;
+                const int nblk = g.nchunks * g.ntg * g.nbsub;
                 for (int b = 0; b < nblk; ++b) {
                     mbar_wait(bar_b_empty + 8 * bs, bph ^ 1);
                     mbar_expect_tx(bar_b_full + 8 * bs, g.b_stage_bytes);
@@ -207,7 +219,7 @@ k_conv_tc(const Args a) {
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.NT >> 3) << 17) | ((128u >> 4) << 24);
             int as = 0, bs = 0, cs = 0; uint32_t aph = 0, bph = 0, cph = 0;
-            const uint32_t sbo_a = g.Wh * 16, lbo_a = g.plane_bytes;
+            const uint32_t sbo_a = g.stride * g.Whh * 16, lbo_a = g.plane_bytes;
             const uint32_t sbo_b = 128, lbo_b = g.NT * 16;
             for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
                 mbar_wait(bar_acc_empty + 8 * cs, cph ^ 1);
@@ -218,17 +230,21 @@ k_conv_tc(const Args a) {
                     mbar_wait(bar_a_full + 8 * as, aph);
                     tc_fence_after();
                     const uint32_t a_st = sA + as * g.a_stage_bytes;
-                    for (int t = 0; t < taps; ++t) {
-                        const uint32_t tap_off = ((t / g.ks) * g.Wh + (t % g.ks)) * 16;
+                    for (int tg = 0; tg < g.ntg; ++tg) {
                         for (int s = 0; s < g.nbsub; ++s) {
                             mbar_wait(bar_b_full + 8 * bs, bph);
                             tc_fence_after();
                             const uint32_t b_st = sB + bs * g.b_stage_bytes;
-                            for (int j = 0; j < g.BC / 8; ++j) {
-                                const uint64_t ad = make_desc(a_st + (s * (g.BC / 4) + 2 * j) * g.plane_bytes + tap_off, lbo_a, sbo_a);
-                                const uint64_t bd = make_desc(b_st + (2 * j) * lbo_b, lbo_b, sbo_b);
-                                tc_mma_tf32(d_tmem, ad, bd, idesc, acc);
-                                acc = 1;
+                            for (int tt = 0; tt < g.TG; ++tt) {
+                                const int t = tg * g.TG + tt;
+                                const int fr = t / g.ks, fs = t - fr * g.ks;
+                                const uint32_t tap_off = ((fs % g.stride) * g.parplane_units + fr * g.Whh + fs / g.stride) * 16;
+                                for (int j = 0; j < g.BC / 8; ++j) {
+                                    const uint64_t ad = make_desc(a_st + (s * (g.BC / 4) + 2 * j) * g.plane_bytes + tap_off, lbo_a, sbo_a);
+                                    const uint64_t bd = make_desc(b_st + (tt * (g.BC / 4) + 2 * j) * lbo_b, lbo_b, sbo_b);
+                                    tc_mma_tf32(d_tmem, ad, bd, idesc, acc);
+                                    acc = 1;
+                                }
                             }
                             tc_commit(bar_b_empty + 8 * bs);
                             if (++bs == g.nb_stages) { bs = 0; bph ^= 1; }
@@ -251,7 +267,7 @@ k_conv_tc(const Args a) {
             const int tw = r % g.tiles_w; r /= g.tiles_w;
             const int th = r % g.tiles_h;
             const int img = r / g.tiles_h;
-            const int h0 = th * kTileH - g.pad, w0 = tw * kTileW - g.pad;
+            const int h0 = th * kTileH * g.stride - g.pad, w0 = tw * kTileW * g.stride - g.pad;
             const float* xi = a.x + (size_t)img * HWC * g.Cin;
             for (int c = 0; c < g.nchunks; ++c) {
                 mbar_wait(bar_a_empty + 8 * as, aph ^ 1);
@@ -269,7 +285,7 @@ k_conv_tc(const Args a) {
                             const int px = it / g.cgA, cg = it - px * g.cgA;
                             const int hh = px / g.Wh, ww = px - hh * g.Wh;
                             const int ih = h0 + hh, iw = w0 + ww;
-                            dst[u] = a_st + cg * g.plane_bytes + px * 16;
+                            dst[u] = a_st + cg * g.plane_bytes + ((ww % g.stride) * g.parplane_units + hh * g.Whh + ww / g.stride) * 16;
                             if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W)
                                 v[u] = __ldg(reinterpret_cast<const float4*>(xc + ((size_t)ih * g.W + iw) * g.Cin + cg * 4));
                         }
@@ -299,8 +315,8 @@ k_conv_tc(const Args a) {
             const int th = r % g.tiles_h;
             const int img = r / g.tiles_h;
             const int oh = th * kTileH + hh, ow = tw * kTileW + ww;
-            const bool valid = oh < g.H && ow < g.W;
-            const size_t pix = ((size_t)img * HWC + (size_t)oh * g.W + ow) * g.Cout;
+            const bool valid = oh < g.Ho && ow < g.Wo;
+            const size_t pix = ((size_t)img * g.Ho * g.Wo + (size_t)oh * g.Wo + ow) * g.Cout;
             const float* bias = a.bias ? a.bias + (size_t)(img % g.wsets) * g.Cout : nullptr;
             mbar_wait(bar_acc_full + 8 * cs, cph);
             tc_fence_after();
@@ -344,21 +360,23 @@ k_conv_tc(const Args a) {
 
 // weight packing: SIMT layout [wsets][ks*ks*Cin][Cout] -> smem-image blocks, TF32-rounded
 __global__ void k_pack(const Geom g, const float* __restrict__ w, float* __restrict__ out) {
-    const long long total = (long long)g.wsets * g.blocks_per_set * g.BC * g.NT;
+    const long long total = (long long)g.wsets * g.blocks_per_set * g.TG * g.BC * g.NT;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int taps = g.ks * g.ks;
-    const int per_block = g.BC * g.NT;
+    const int per_block = g.TG * g.BC * g.NT;
     long long blk = i / per_block;
     int e = (int)(i % per_block);
     const int j = e & 3; e >>= 2;
-    const int n = e % g.NT;
-    const int kg = e / g.NT;
+    const int n = e % g.NT; e /= g.NT;
+    const int kg = e % (g.BC / 4);
+    const int tt = e / (g.BC / 4);
     const int s = (int)(blk % g.nbsub); blk /= g.nbsub;
-    const int t = (int)(blk % taps); blk /= taps;
+    const int tgi = (int)(blk % g.ntg); blk /= g.ntg;
     const int c = (int)(blk % g.nchunks); blk /= g.nchunks;
     const int nt = (int)(blk % g.ntn);
     const int ws = (int)(blk / g.ntn);
+    const int t = tgi * g.TG + tt;
     const int cin = c * g.AC + s * g.BC + kg * 4 + j;
     const int co = nt * g.NT + n;
     float v = 0.f;
@@ -407,7 +425,7 @@ extern "C" int danet_conv_tc_pack(const danet_conv_desc* d, const float* w_simt,
     tc::Geom g;
     DANET_CHECK(d && tc::make_geom(d, &g), "danet_conv_tc_pack: shape not supported by the tcgen05 path");
     DANET_CHECK(w_simt && w_packed, "danet_conv_tc_pack: null pointer");
-    const long long total = (long long)g.wsets * g.blocks_per_set * g.BC * g.NT;
+    const long long total = (long long)g.wsets * g.blocks_per_set * g.TG * g.BC * g.NT;
     tc::k_pack<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g, w_simt, (float*)w_packed);
     DANET_LAUNCH_CHECK();
     return 0;

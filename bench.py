@@ -305,6 +305,7 @@ def profile_step(net, plan, x, dev):
     plan.use_cuda_graph = False
     ops = plan.ops
     events = []
+    shapes = []
 
     class Timed(object):
         def __getattr__(self, name):
@@ -320,6 +321,8 @@ def profile_step(net, plan, x, dev):
                 tag = name
                 if name == "conv2d":
                     tag = "conv_tc" if a[1] == 1 else "conv_simt"
+                    d = a[0]
+                    shapes.append((tag, d["N"], d["H"], d["Cin"], d["Cout"], d["ksize"], d["stride"], d["wsets"]))
                 events.append((tag, e0, e1))
                 return r
             return wrapped
@@ -332,6 +335,20 @@ def profile_step(net, plan, x, dev):
     for tag, e0, e1 in events:
         agg[tag] = agg.get(tag, 0.0) + e0.elapsed_time(e1)
     conv_ms = agg.get("conv_tc", 0.0) + agg.get("conv_simt", 0.0)
+    per_shape = {}
+    ci = 0
+    for tag, e0, e1 in events:
+        if tag.startswith("conv"):
+            key = "%s N%d H%d Cin%d Cout%d k%d s%d g%d" % shapes[ci]
+            ent = per_shape.setdefault(key, [0, 0.0])
+            ent[0] += 1; ent[1] += e0.elapsed_time(e1)
+            ci += 1
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "conv_profile.json"), "w") as f:
+            json.dump(sorted(([k] + v for k, v in per_shape.items()), key=lambda r: -r[2]), f, indent=0)
+    except Exception:
+        pass
     n_conv = sum(1 for t, _, _ in events if t.startswith("conv"))
     kern = "k_conv_tc (tcgen05 TF32) + k_conv_simt" if agg.get("conv_tc") else "k_conv_simt (fp32 FMA implicit GEMM)"
     return {"conv_ms": conv_ms, "n_conv": n_conv, "conv_kernel": kern,

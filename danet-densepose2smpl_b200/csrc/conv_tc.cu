@@ -27,10 +27,12 @@ namespace danet {
 namespace tc {
 
 constexpr int kTileH = 16, kTileW = 8;
-constexpr int kThreads = 320;            // warp0: B producer, warp1: MMA + TMEM alloc, warps 2-5: A producers, warps 6-9: epilogue
-constexpr int kNumProducers = 128;
-constexpr int kMaxBStages = 8;
-constexpr int kSmemBudget = 200 * 1024;
+constexpr int kThreads = 448;            // warp0: B producer, warp1: MMA + TMEM alloc, warps 2-9: A producers, warps 10-13: epilogue
+constexpr int kNumProducers = 256;
+constexpr int kMaxBStages = 16;
+constexpr int kSmemBudget = 200 * 1024;  // one CTA per SM
+constexpr int kSmemHalf = 100 * 1024;    // two CTAs per SM when everything fits
+constexpr bool kAllowTwoCtas = false;    // needs <= 73 registers/thread (currently 113): off
 
 struct Geom {
     int N, H, W, Cin, Cout, ks, pad, stride, relu, wsets;
@@ -42,6 +44,7 @@ struct Geom {
     int tiles_w, tiles_h, total_tiles;
     int a_stage_bytes, b_stage_bytes, nb_stages;
     int smem_bytes;
+    int tmem_cols, ctas_per_sm, b_resident, CGT;
     long long blocks_per_set;            // packed weight blocks per weight set
 };
 
@@ -74,13 +77,32 @@ static bool make_geom(const danet_conv_desc* d, Geom* g) {
     for (int t = taps; t >= 1; --t) if (taps % t == 0 && t * tap_bytes <= 32 * 1024) { tg = t; break; }
     g->TG = tg; g->ntg = taps / tg;
     g->b_stage_bytes = tg * tap_bytes;
-    int nb = (kSmemBudget - 2 * g->a_stage_bytes) / g->b_stage_bytes;
-    if (nb < 2) return false;
-    g->nb_stages = nb > kMaxBStages ? kMaxBStages : nb;
     g->tiles_w = (g->Wo + kTileW - 1) / kTileW; g->tiles_h = (g->Ho + kTileH - 1) / kTileH;
     g->total_tiles = d->N * g->tiles_h * g->tiles_w * g->ntn;
-    g->smem_bytes = 2 * g->a_stage_bytes + g->nb_stages * g->b_stage_bytes + 256 + 1024;
-    if (g->smem_bytes < 120 * 1024) g->smem_bytes = 120 * 1024;      // one CTA per SM: each CTA allocates all 512 TMEM columns
+    int cols = 32;
+    while (cols < 2 * g->NT) cols *= 2;
+    g->tmem_cols = cols;
+    int cgt = 2;
+    while (cgt < g->cgA) cgt *= 2;
+    g->CGT = cgt;
+    const int nblk = g->nchunks * g->ntg * g->nbsub;
+    const int fixed = 2 * g->a_stage_bytes + 512 + 1024;
+    g->b_resident = 0;
+    if (d->wsets == 1 && g->ntn == 1 && nblk <= kMaxBStages && fixed + nblk * g->b_stage_bytes <= kSmemBudget &&
+        g->total_tiles >= 2 * 148) {
+        // the whole weight set stays in shared memory for the lifetime of the CTA
+        g->b_resident = 1; g->nb_stages = nblk; g->ctas_per_sm = 1;
+        if (kAllowTwoCtas && fixed + nblk * g->b_stage_bytes <= kSmemHalf && g->tmem_cols <= 256) g->ctas_per_sm = 2;
+    } else {
+        int budget = kSmemBudget; g->ctas_per_sm = 1;
+        if (kAllowTwoCtas && g->tmem_cols <= 256 && (kSmemHalf - fixed) / g->b_stage_bytes >= 3) { budget = kSmemHalf; g->ctas_per_sm = 2; }
+        int nb = (budget - fixed) / g->b_stage_bytes;
+        if (nb < 2) return false;
+        g->nb_stages = nb > kMaxBStages ? kMaxBStages : nb;
+    }
+    g->smem_bytes = fixed + g->nb_stages * g->b_stage_bytes;
+    const int floor_bytes = g->ctas_per_sm == 2 ? 60 * 1024 : 120 * 1024;      // pin the occupancy the TMEM budget assumes
+    if (g->smem_bytes < floor_bytes) g->smem_bytes = floor_bytes;
     g->blocks_per_set = (long long)g->ntn * g->nchunks * g->ntg * g->nbsub;
     return true;
 }
@@ -139,6 +161,16 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ float to_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -170,7 +202,7 @@ k_conv_tc(const Args a) {
     // barrier map (8 bytes each)
     const uint32_t bar_a_full = sBar, bar_a_empty = sBar + 16, bar_acc_full = sBar + 32, bar_acc_empty = sBar + 48;
     const uint32_t bar_b_full = sBar + 64, bar_b_empty = sBar + 64 + 8 * kMaxBStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (sBar - sbase) + 64 + 16 * kMaxBStages);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (sBar - sbase) + 64 + 16 * kMaxBStages);   // 64 + 256 + 4 <= 512
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -184,7 +216,7 @@ k_conv_tc(const Args a) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)g.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -206,8 +238,9 @@ k_conv_tc(const Args a) {
                 const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wpk) +
                     ((long long)ws * g.blocks_per_set + (long long)nt * g.nchunks * g.ntg * g.nbsub) * g.b_stage_bytes;
                 const int nblk = g.nchunks * g.ntg * g.nbsub;
+                if (g.b_resident && tile != (int)blockIdx.x) break;          // weights already resident
                 for (int b = 0; b < nblk; ++b) {
-                    mbar_wait(bar_b_empty + 8 * bs, bph ^ 1);
+                    if (!g.b_resident) mbar_wait(bar_b_empty + 8 * bs, bph ^ 1);
                     mbar_expect_tx(bar_b_full + 8 * bs, g.b_stage_bytes);
                     bulk_g2s(sB + bs * g.b_stage_bytes, src + (long long)b * g.b_stage_bytes, g.b_stage_bytes, bar_b_full + 8 * bs);
                     if (++bs == g.nb_stages) { bs = 0; bph ^= 1; }
@@ -232,7 +265,7 @@ k_conv_tc(const Args a) {
                     const uint32_t a_st = sA + as * g.a_stage_bytes;
                     for (int tg = 0; tg < g.ntg; ++tg) {
                         for (int s = 0; s < g.nbsub; ++s) {
-                            mbar_wait(bar_b_full + 8 * bs, bph);
+                            mbar_wait(bar_b_full + 8 * bs, g.b_resident ? 0u : bph);
                             tc_fence_after();
                             const uint32_t b_st = sB + bs * g.b_stage_bytes;
                             for (int tt = 0; tt < g.TG; ++tt) {
@@ -246,7 +279,7 @@ k_conv_tc(const Args a) {
                                     acc = 1;
                                 }
                             }
-                            tc_commit(bar_b_empty + 8 * bs);
+                            if (!g.b_resident) tc_commit(bar_b_empty + 8 * bs);
                             if (++bs == g.nb_stages) { bs = 0; bph ^= 1; }
                         }
                     }
@@ -257,10 +290,20 @@ k_conv_tc(const Args a) {
                 if (++cs == 2) { cs = 0; cph ^= 1; }
             }
         }
-    } else if (warp < 6) {
+    } else if (warp < 10) {
         // ================= A producers: halo tile -> smem (no-swizzle K-major) =================
-        const int pt = threadIdx.x - 64;                        // 0..127
-        const int items = g.npx * g.cgA;
+        // thread <-> (channel group cg, pixel slot); pixels advance by a fixed step per pass so the
+        // halo coordinates are updated incrementally (no divisions in the loop); every pass's
+        // global load is issued before the first shared store (one latency exposure per 8 passes).
+        const int pt = threadIdx.x - 64;                        // 0..255
+        const int cg = pt & (g.CGT - 1);
+        const int ppt = kNumProducers / g.CGT;                   // pixels per pass
+        const int px0 = pt / g.CGT;
+        const int hh0 = px0 / g.Wh, ww0 = px0 - hh0 * g.Wh;
+        const int dhh = ppt / g.Wh, dww = ppt - dhh * g.Wh;
+        const int npass = (g.npx + ppt - 1) / ppt;
+        const bool cg_ok = cg < g.cgA;
+        const int sshift = g.stride - 1;                         // stride 1 -> 0, stride 2 -> 1
         int as = 0; uint32_t aph = 0;
         for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
             int r = tile / g.ntn;
@@ -268,30 +311,30 @@ k_conv_tc(const Args a) {
             const int th = r % g.tiles_h;
             const int img = r / g.tiles_h;
             const int h0 = th * kTileH * g.stride - g.pad, w0 = tw * kTileW * g.stride - g.pad;
-            const float* xi = a.x + (size_t)img * HWC * g.Cin;
+            const float* xi = a.x + (size_t)img * HWC * g.Cin + cg * 4;
             for (int c = 0; c < g.nchunks; ++c) {
                 mbar_wait(bar_a_empty + 8 * as, aph ^ 1);
-                const uint32_t a_st = sA + as * g.a_stage_bytes;
+                const uint32_t a_st = sA + as * g.a_stage_bytes + cg * g.plane_bytes;
                 const float* xc = xi + c * g.AC;
-                for (int it0 = pt; it0 < items; it0 += kNumProducers * 4) {
-                    float4 v[4];
-                    uint32_t dst[4];
+                int hh = hh0, ww = ww0;
+                for (int p0 = 0; p0 < npass; p0 += 8) {
+                    float4 v[8];
+                    uint32_t dst[8];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int it = it0 + u * kNumProducers;
+                    for (int u = 0; u < 8; ++u) {
                         v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                         dst[u] = 0xFFFFFFFFu;
-                        if (it < items) {
-                            const int px = it / g.cgA, cg = it - px * g.cgA;
-                            const int hh = px / g.Wh, ww = px - hh * g.Wh;
+                        if (p0 + u < npass && hh < g.Hh && cg_ok) {
                             const int ih = h0 + hh, iw = w0 + ww;
-                            dst[u] = a_st + cg * g.plane_bytes + ((ww % g.stride) * g.parplane_units + hh * g.Whh + ww / g.stride) * 16;
+                            dst[u] = a_st + (((ww & sshift) * g.parplane_units) + hh * g.Whh + (ww >> sshift)) * 16;
                             if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W)
-                                v[u] = __ldg(reinterpret_cast<const float4*>(xc + ((size_t)ih * g.W + iw) * g.Cin + cg * 4));
+                                v[u] = __ldg(reinterpret_cast<const float4*>(xc + ((size_t)ih * g.W + iw) * g.Cin));
                         }
+                        ww += dww; hh += dhh;
+                        if (ww >= g.Wh) { ww -= g.Wh; hh += 1; }
                     }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
+                    for (int u = 0; u < 8; ++u) {
                         if (dst[u] != 0xFFFFFFFFu)
                             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst[u]), "f"(to_tf32(v[u].x)),
                                          "f"(to_tf32(v[u].y)), "f"(to_tf32(v[u].z)), "f"(to_tf32(v[u].w)) : "memory");
@@ -304,7 +347,7 @@ k_conv_tc(const Args a) {
         }
     } else {
         // ================= epilogue: TMEM -> bias/residual/ReLU -> global =================
-        const int q = warp & 3;                                  // TMEM lane quarter this warp may access
+        const int q = warp & 3;                                  // TMEM lane quarter this warp may access (warps 10..13 -> 2,3,0,1)
         const int m = q * 32 + lane;
         const int hh = m >> 3, ww = m & 7;
         int cs = 0; uint32_t cph = 0;
@@ -321,24 +364,32 @@ k_conv_tc(const Args a) {
             mbar_wait(bar_acc_full + 8 * cs, cph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cs * g.NT;
-            for (int c0 = 0; c0 < g.NT; c0 += 16) {
-                float v[16];
-                tc_ld16(taddr + c0, v);
+            for (int c0 = 0; c0 < g.NT; c0 += 32) {
                 const int ch0 = nt * g.NT + c0;
+                const bool second = c0 + 16 < g.NT;               // NT is a multiple of 16
+                float4 rr[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    rr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int ch = ch0 + 4 * j;
+                    if (a.res && valid && ch < g.Cout && (j < 4 || second))
+                        rr[j] = __ldg(reinterpret_cast<const float4*>(a.res + pix + ch));
+                }
+                float v[32];
+                tc_ld16_nowait(taddr + c0, v);
+                if (second) tc_ld16_nowait(taddr + c0 + 16, v + 16);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (valid) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
+                    for (int j = 0; j < 8; ++j) {
                         const int ch = ch0 + 4 * j;
-                        if (ch < g.Cout) {
-                            float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        if (ch < g.Cout && (j < 4 || second)) {
+                            float4 o = make_float4(__uint_as_float(__float_as_uint(v[4 * j])), v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                             if (bias) {
                                 const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + ch));
                                 o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
                             }
-                            if (a.res) {
-                                const float4 rr = __ldg(reinterpret_cast<const float4*>(a.res + pix + ch));
-                                o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-                            }
+                            o.x += rr[j].x; o.y += rr[j].y; o.z += rr[j].z; o.w += rr[j].w;
                             if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
                             *reinterpret_cast<float4*>(a.y + pix + ch) = o;
                         }
@@ -354,7 +405,7 @@ k_conv_tc(const Args a) {
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols) : "memory");
     }
 }
 
@@ -400,7 +451,8 @@ int conv_tc_launch(const danet_conv_desc* d, const float* x, const void* w_packe
         DANET_CUDA(cudaFuncSetAttribute(tc::k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    const int grid = a.g.total_tiles < sm_count ? a.g.total_tiles : sm_count;
+    const int cap = sm_count * a.g.ctas_per_sm;
+    const int grid = a.g.total_tiles < cap ? a.g.total_tiles : cap;
     tc::k_conv_tc<<<grid, tc::kThreads, a.g.smem_bytes, stream>>>(a);
     DANET_LAUNCH_CHECK();
     return 0;

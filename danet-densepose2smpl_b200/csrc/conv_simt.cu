@@ -4,7 +4,7 @@
 // models/module/res_module.py; grouped convolutions (res_module.py:335-342,500-535) are expressed
 // as `wsets` weight sets over the (batch,part)-flattened image axis (see include/danet_b200.h).
 //
-// CTA tile: 64 output pixels of one image x 64 output channels, 256 threads, 4x4 outputs per
+// CTA tile: 64 (image, output pixel) rows of one weight set x 64 output channels, 256 threads, 4x4 outputs per
 // thread, K streamed in (tap, 16-channel) chunks through shared memory with register prefetch.
 #include "common.cuh"
 
@@ -24,21 +24,24 @@ __global__ void __launch_bounds__(256)
 k_conv_simt(ConvArgs a) {
     __shared__ __align__(16) float As[kKC][kAPitch];
     __shared__ __align__(16) float Bs[kKC][kTCo];
+    // rows of the implicit GEMM = (image of this weight set, output pixel), flattened: image
+    // n = g + wsets * (row / HoWo).  Tiny maps (4x4, 2x2) then still fill the 64-row tile.
     const int tid = threadIdx.x;
-    const int n = blockIdx.z;
+    const int g = blockIdx.z;
     const int q0 = blockIdx.x * kTP;
     const int co0 = blockIdx.y * kTCo;
     const int HoWo = a.Ho * a.Wo;
-    const int g = n % a.wsets;
+    const int rows = ((a.N - g + a.wsets - 1) / a.wsets) * HoWo;
     const int K = a.ks * a.ks * a.Cin;
     const float* wg = a.w + (size_t)g * K * a.Cout;
-    const float* xn = a.x + (size_t)n * a.H * a.W * a.Cin;
 
-    // A-load role: pixel lp = tid/4, channel vec lv = tid%4
+    // A-load role: row lp = tid/4, channel vec lv = tid%4
     const int lp = tid >> 2, lv = tid & 3;
     const int lq = q0 + lp;
-    const bool lvalid = lq < HoWo;
-    const int loh = lvalid ? lq / a.Wo : 0, low = lvalid ? lq % a.Wo : 0;
+    const bool lvalid = lq < rows;
+    const int lk = lvalid ? lq / HoWo : 0, lpix = lvalid ? lq - lk * HoWo : 0;
+    const int loh = lpix / a.Wo, low = lpix - loh * a.Wo;
+    const float* xn = a.x + (size_t)(g + a.wsets * lk) * a.H * a.W * a.Cin;
     // B-load role: row bk = tid/16, col vec bv = tid%16
     const int bk = tid >> 4, bv = tid & 15;
     // compute role
@@ -95,8 +98,9 @@ k_conv_simt(ConvArgs a) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int q = q0 + ty * 4 + i;
-        if (q >= HoWo) continue;
-        const size_t o = ((size_t)n * HoWo + q) * a.Cout + co;
+        if (q >= rows) continue;
+        const int qk = q / HoWo, qp = q - qk * HoWo;
+        const size_t o = ((size_t)(g + a.wsets * qk) * HoWo + qp) * a.Cout + co;
         float4 v = make_float4(acc[i][0] + bias.x, acc[i][1] + bias.y, acc[i][2] + bias.z, acc[i][3] + bias.w);
         if (a.res) {
             const float4 rr = __ldg(reinterpret_cast<const float4*>(a.res + o));
@@ -115,7 +119,8 @@ int conv_simt_launch(const danet_conv_desc* d, const float* x, const float* w, c
     a.Ho = (d->H + 2 * d->pad - d->ksize) / d->stride + 1;
     a.Wo = (d->W + 2 * d->pad - d->ksize) / d->stride + 1;
     a.x = x; a.w = w; a.bias = bias; a.res = residual; a.y = y;
-    dim3 grid(cdiv(a.Ho * a.Wo, kTP), cdiv(a.Cout, kTCo), a.N);
+    const int rows = cdiv(a.N, a.wsets) * a.Ho * a.Wo;
+    dim3 grid(cdiv(rows, kTP), cdiv(a.Cout, kTCo), a.wsets);
     k_conv_simt<<<grid, 256, 0, stream>>>(a);
     DANET_LAUNCH_CHECK();
     return 0;
@@ -135,7 +140,7 @@ static int check_conv_desc(const danet_conv_desc* d) {
     DANET_CHECK(d->ksize >= 1 && d->ksize <= 7 && d->stride >= 1 && d->stride <= 2 && d->pad >= 0, "danet_conv2d: bad ksize/stride/pad");
     DANET_CHECK(d->wsets >= 1, "danet_conv2d: wsets must be >= 1");
     DANET_CHECK(d->H + 2 * d->pad >= d->ksize && d->W + 2 * d->pad >= d->ksize, "danet_conv2d: kernel larger than padded input");
-    DANET_CHECK(d->N <= 65535, "danet_conv2d: N=%d exceeds 65535 images per launch", d->N);
+    DANET_CHECK(d->wsets <= 65535, "danet_conv2d: wsets=%d exceeds 65535", d->wsets);
     return 0;
 }
 

@@ -490,7 +490,7 @@ int conv_tc_launch(const danet_conv_desc* d, const float* x, const void* w_packe
         int dev = 0;
         DANET_CUDA(cudaGetDevice(&dev));
         DANET_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-        DANET_CUDA(cudaFuncSetAttribute(tc::k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        DANET_CUDA(cudaFuncSetAttribute(tc::k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr_set = true;
     }
     const int cap = sm_count * a.g.ctas_per_sm;

@@ -6,8 +6,10 @@
 //   M tile  = 128 output pixels = 16 rows x 8 columns of one image; N tile = up to 256 output
 //             channels; accumulators live in TMEM (double-buffered).
 //   A (activations): the input HALO of the tile ((15*s+k) x (7*s+k) pixels) is loaded ONCE per
-//             channel chunk by 8 producer warps (coalesced 16-byte global loads, TF32 rounding,
-//             16-byte st.shared) into a SWIZZLED K-major UMMA layout: one row per halo pixel,
+//             channel chunk by 8 producer warps (16-byte cp.async with zero fill, completion signalled
+//             by cp.async.mbarrier.arrive.noinc -- the producers never block on their own loads; the
+//             tensor core truncates fp32 to TF32, so every TC epilogue stores RN-rounded TF32 values
+//             and the next layer's operands are exact) into a SWIZZLED K-major UMMA layout: one row per halo pixel,
 //             SWB = 128/64/32 bytes (32/16/8 channels) per row, 16-byte chunks XOR-swizzled by the
 //             row phase exactly like TMA's SWIZZLE_128B/64B/32B, halo rows padded to a pitch of
 //             WP = 8k pixels so that every 8-row MMA group starts at the same swizzle phase.
@@ -301,6 +303,7 @@ k_conv_tc(const Args a) {
                 uint32_t acc = 0;
                 for (int c = 0; c < g.nchunks; ++c) {
                     mbar_wait(bar_a_full + 8 * as, aph);
+                    fence_proxy_async();                      // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
                     tc_fence_after();
                     const uint32_t a_st16 = (sA + as * g.a_stage_bytes) >> 4;
                     int t = 0;
@@ -356,32 +359,23 @@ k_conv_tc(const Args a) {
                 const bool ch_ok = c * g.KCH + cg * 4 < g.Cin;       // channels beyond Cin are zero-filled in smem
                 const float* xc = xi + c * g.KCH;
                 int hh = hh0, ww = ww0;
-                for (int p0 = 0; p0 < npass; p0 += 8) {
-                    float4 v[8];
-                    uint32_t dst[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        dst[u] = 0xFFFFFFFFu;
-                        if (p0 + u < npass && hh < g.Hh) {
-                            const int ih = h0 + hh, iw = w0 + ww;
-                            const uint32_t row = (ww & sshift) * g.plane_rows + hh * g.WP + (ww >> sshift);
-                            dst[u] = a_st + swz(row * g.SWB + cg * 16, smask);
-                            if (ch_ok && ih >= 0 && ih < g.H && iw >= 0 && iw < g.W)
-                                v[u] = __ldg(reinterpret_cast<const float4*>(xc + ((size_t)ih * g.W + iw) * g.Cin));
-                        }
-                        ww += dww; hh += dhh;
-                        if (ww >= g.Wh) { ww -= g.Wh; hh += 1; }
+                // fully asynchronous: every 16-byte piece is a cp.async (zero-filled when it is padding or a
+                // channel beyond Cin); the stage barrier is armed with cp.async.mbarrier.arrive.noinc, so
+                // the producer never waits for its own loads and runs up to na_stages ahead of the MMAs.
+#pragma unroll 4
+                for (int p = 0; p < npass; ++p) {
+                    if (hh < g.Hh) {
+                        const int ih = h0 + hh, iw = w0 + ww;
+                        const uint32_t row = (ww & sshift) * g.plane_rows + hh * g.WP + (ww >> sshift);
+                        const uint32_t dst = a_st + swz(row * g.SWB + cg * 16, smask);
+                        const bool ok = ch_ok && ih >= 0 && ih < g.H && iw >= 0 && iw < g.W;
+                        const float* src = ok ? xc + ((size_t)ih * g.W + iw) * g.Cin : a.x;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16u : 0u) : "memory");
                     }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        if (dst[u] != 0xFFFFFFFFu)
-                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst[u]), "f"(to_tf32(v[u].x)),
-                                         "f"(to_tf32(v[u].y)), "f"(to_tf32(v[u].z)), "f"(to_tf32(v[u].w)) : "memory");
-                    }
+                    ww += dww; hh += dhh;
+                    if (ww >= g.Wh) { ww -= g.Wh; hh += 1; }
                 }
-                fence_proxy_async();
-                mbar_arrive(bar_a_full + 8 * as);
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_a_full + 8 * as) : "memory");
                 if (++as == g.na_stages) { as = 0; aph ^= 1; }
             }
         }
@@ -431,6 +425,7 @@ k_conv_tc(const Args a) {
                             }
                             o.x += rr[j].x; o.y += rr[j].y; o.z += rr[j].z; o.w += rr[j].w;
                             if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                            o.x = to_tf32(o.x); o.y = to_tf32(o.y); o.z = to_tf32(o.z); o.w = to_tf32(o.w);
                             *reinterpret_cast<float4*>(a.y + pix + ch) = o;
                         }
                     }

@@ -55,6 +55,7 @@ struct Geom {
     int a_stage_bytes, b_stage_bytes, tap_bytes, nb_stages, na_stages;
     int smem_bytes;
     int tmem_cols, ctas_per_sm, b_resident, variant;
+    int KS, acc_stages;                  // independent accumulators per tile (K split), TMEM accumulator stages
     long long blocks_per_set;            // packed weight blocks per weight set
 };
 
@@ -81,8 +82,13 @@ static bool make_geom(const danet_conv_desc* d, Geom* g) {
     g->NT = ((np + g->ntn - 1) / g->ntn + 15) / 16 * 16;
     g->tiles_w = (g->Wo + kTileW - 1) / kTileW; g->tiles_h = (g->Ho + kTileH - 1) / kTileH;
     g->total_tiles = d->N * g->tiles_h * g->tiles_w * g->ntn;
+    // Consecutive tcgen05.mma on ONE accumulator are serialised by the accumulate dependency
+    // (~250-450 cycles each for these narrow N, measured); the K loop is therefore dealt round-robin
+    // over KS independent TMEM accumulators that the epilogue sums.
+    g->KS = g->NT <= 64 ? 4 : 2;
+    g->acc_stages = (2 * g->KS * g->NT <= 512) ? 2 : 1;
     int cols = 32;
-    while (cols < 2 * g->NT) cols *= 2;
+    while (cols < g->acc_stages * g->KS * g->NT) cols *= 2;
     g->tmem_cols = cols;
     const int taps = d->ksize * d->ksize;
     const int fixed = 512 + 1024;
@@ -102,6 +108,7 @@ static bool make_geom(const danet_conv_desc* d, Geom* g) {
         }
     }
     if (!ok) return false;
+    while (g->KS > 1 && g->nchunks * taps * (g->KCH / 8) < g->KS) g->KS /= 2;
     const int nblk = g->nchunks * g->ntg;
     g->na_stages = 2;
     g->b_resident = 0; g->ctas_per_sm = 1;
@@ -240,7 +247,7 @@ k_conv_tc(const Args a) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full + 8 * i, 1); mbar_init(bar_acc_empty + 8 * i, 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full + 8 * i, 1); mbar_init(bar_acc_empty + 8 * i, 128); }   // stage 1 unused when acc_stages == 1
         for (int i = 0; i < g.na_stages; ++i) { mbar_init(bar_a_full + 8 * i, kNumProducers); mbar_init(bar_a_empty + 8 * i, 1); }
         for (int i = 0; i < g.nb_stages; ++i) { mbar_init(bar_b_full + 8 * i, 1); mbar_init(bar_b_empty + 8 * i, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -299,8 +306,8 @@ k_conv_tc(const Args a) {
             for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
                 mbar_wait(bar_acc_empty + 8 * cs, cph ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + cs * g.NT;
-                uint32_t acc = 0;
+                const uint32_t d_base = tmem_base + cs * (g.KS * g.NT);
+                uint32_t nmma = 0;
                 for (int c = 0; c < g.nchunks; ++c) {
                     mbar_wait(bar_a_full + 8 * as, aph);
                     fence_proxy_async();                      // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
@@ -316,8 +323,8 @@ k_conv_tc(const Args a) {
                             for (int j = 0; j < kmma; ++j) {
                                 const uint64_t ad = ad_hi | (uint64_t)(((a16 + 2 * j) & 0x3FFFu) | lo_fixed);
                                 const uint64_t bd = bd_hi | (uint64_t)(((b16 + 2 * j) & 0x3FFFu) | lo_fixed);
-                                tc_mma_tf32(d_tmem, ad, bd, idesc, acc);
-                                acc = 1;
+                                tc_mma_tf32(d_base + (nmma & (uint32_t)(g.KS - 1)) * g.NT, ad, bd, idesc, nmma >= (uint32_t)g.KS);
+                                ++nmma;
                             }
                             b16 += g.tap_bytes >> 4;
                         }
@@ -328,7 +335,7 @@ k_conv_tc(const Args a) {
                     if (++as == g.na_stages) { as = 0; aph ^= 1; }
                 }
                 tc_commit(bar_acc_full + 8 * cs);
-                if (++cs == 2) { cs = 0; cph ^= 1; }
+                if (++cs == g.acc_stages) { cs = 0; cph ^= 1; }
             }
         }
     } else if (warp < kWarpEpi) {
@@ -397,28 +404,35 @@ k_conv_tc(const Args a) {
             const float* bias = a.bias ? a.bias + (size_t)(img % g.wsets) * g.Cout : nullptr;
             mbar_wait_sleep(bar_acc_full + 8 * cs, cph);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cs * g.NT;
-            for (int c0 = 0; c0 < g.NT; c0 += 32) {
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cs * (g.KS * g.NT);
+            for (int c0 = 0; c0 < g.NT; c0 += 16) {
                 const int ch0 = nt * g.NT + c0;
-                const bool second = c0 + 16 < g.NT;               // NT is a multiple of 16
-                float4 rr[8];
+                float4 rr[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < 4; ++j) {
                     rr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                     const int ch = ch0 + 4 * j;
-                    if (a.res && valid && ch < g.Cout && (j < 4 || second))
-                        rr[j] = __ldg(reinterpret_cast<const float4*>(a.res + pix + ch));
+                    if (a.res && valid && ch < g.Cout) rr[j] = __ldg(reinterpret_cast<const float4*>(a.res + pix + ch));
                 }
-                float v[32];
-                tc_ld16_nowait(taddr + c0, v);
-                if (second) tc_ld16_nowait(taddr + c0 + 16, v + 16);
+                float v[4][16];
+                tc_ld16_nowait(taddr + c0, v[0]);
+                if (g.KS > 1) tc_ld16_nowait(taddr + g.NT + c0, v[1]);
+                if (g.KS > 2) { tc_ld16_nowait(taddr + 2 * g.NT + c0, v[2]); tc_ld16_nowait(taddr + 3 * g.NT + c0, v[3]); }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (g.KS > 1) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[0][e] += v[1][e];
+                }
+                if (g.KS > 2) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[0][e] += v[2][e] + v[3][e];
+                }
                 if (valid) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
+                    for (int j = 0; j < 4; ++j) {
                         const int ch = ch0 + 4 * j;
-                        if (ch < g.Cout && (j < 4 || second)) {
-                            float4 o = make_float4(__uint_as_float(__float_as_uint(v[4 * j])), v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        if (ch < g.Cout) {
+                            float4 o = make_float4(v[0][4 * j], v[0][4 * j + 1], v[0][4 * j + 2], v[0][4 * j + 3]);
                             if (bias) {
                                 const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + ch));
                                 o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
@@ -433,7 +447,7 @@ k_conv_tc(const Args a) {
             }
             tc_fence_before();
             mbar_arrive(bar_acc_empty + 8 * cs);
-            if (++cs == 2) { cs = 0; cph ^= 1; }
+            if (++cs == g.acc_stages) { cs = 0; cph ^= 1; }
         }
     }
     tc_fence_before();

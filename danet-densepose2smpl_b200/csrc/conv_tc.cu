@@ -85,7 +85,7 @@ static bool make_geom(const danet_conv_desc* d, Geom* g) {
     // Consecutive tcgen05.mma on ONE accumulator are serialised by the accumulate dependency
     // (~250-450 cycles each for these narrow N, measured); the K loop is therefore dealt round-robin
     // over KS independent TMEM accumulators that the epilogue sums.
-    g->KS = g->NT <= 64 ? 4 : 2;
+    g->KS = 1;      // >1 deals the K loop over independent accumulators (measured: no gain; the limiter was MMA issue)
     g->acc_stages = (2 * g->KS * g->NT <= 512) ? 2 : 1;
     int cols = 32;
     while (cols < g->acc_stages * g->KS * g->NT) cols *= 2;
@@ -187,6 +187,11 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uin
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
     uint32_t r[16];
@@ -293,16 +298,20 @@ k_conv_tc(const Args a) {
         }
     } else if (warp == kWarpMma) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        // The whole warp runs the loop (warp-uniform control flow keeps descriptors in uniform
+        // registers); one elected lane issues the tcgen05 instructions.  A divergent `lane == 0`
+        // region made ptxas wrap every UTCHMMA in an ELECT/BRA.U.ANY loop: ~30 SASS instructions
+        // and ~240 cycles per MMA (profiles/r01_ncu_conv_tc_v6_summary.txt).
+        {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.NT >> 3) << 17) | ((128u >> 4) << 24);
             int as = 0, bs = 0, cs = 0; uint32_t aph = 0, bph = 0, cph = 0;
             const uint32_t sbo_a = g.stride * g.WP * g.SWB, sbo_b = 8 * g.SWB;
             const uint32_t ltype = g.SWB == 128 ? 2u : (g.SWB == 64 ? 4u : 6u);
-            // descriptor high words are loop invariant; the low word only changes in its address field
             const uint64_t ad_hi = make_desc(0, sbo_a, ltype, 0u) & 0xFFFFFFFF00000000ull;
             const uint64_t bd_hi = make_desc(0, sbo_b, ltype, 0u) & 0xFFFFFFFF00000000ull;
             const uint32_t lo_fixed = 1u << 16;
             const int kmma = g.KCH / 8;
+            const uint32_t tap16 = g.tap_bytes >> 4;
             for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
                 mbar_wait(bar_acc_empty + 8 * cs, cph ^ 1);
                 tc_fence_after();
@@ -317,24 +326,32 @@ k_conv_tc(const Args a) {
                     for (int tg = 0; tg < g.ntg; ++tg) {
                         mbar_wait(bar_b_full + 8 * bs, g.b_resident ? 0u : bph);
                         tc_fence_after();
-                        uint32_t b16 = (sB + bs * g.b_stage_bytes) >> 4;
-                        for (int tt = 0; tt < g.TG; ++tt, ++t) {
-                            uint32_t a16 = a_st16 + s_tapoff[t];
-                            for (int j = 0; j < kmma; ++j) {
-                                const uint64_t ad = ad_hi | (uint64_t)(((a16 + 2 * j) & 0x3FFFu) | lo_fixed);
-                                const uint64_t bd = bd_hi | (uint64_t)(((b16 + 2 * j) & 0x3FFFu) | lo_fixed);
-                                tc_mma_tf32(d_base + (nmma & (uint32_t)(g.KS - 1)) * g.NT, ad, bd, idesc, nmma >= (uint32_t)g.KS);
-                                ++nmma;
+                        const uint32_t b16 = (sB + bs * g.b_stage_bytes) >> 4;
+                        if (elect_one()) {
+                            uint32_t bt = b16;
+                            for (int tt = 0; tt < g.TG; ++tt) {
+                                const uint32_t a16 = a_st16 + s_tapoff[t + tt];
+                                for (int j = 0; j < kmma; ++j) {
+                                    const uint64_t ad = ad_hi | (uint64_t)(((a16 + 2 * j) & 0x3FFFu) | lo_fixed);
+                                    const uint64_t bd = bd_hi | (uint64_t)(((bt + 2 * j) & 0x3FFFu) | lo_fixed);
+                                    const uint32_t n = nmma + (uint32_t)(tt * kmma + j);
+                                    tc_mma_tf32(d_base + (n & (uint32_t)(g.KS - 1)) * g.NT, ad, bd, idesc, n >= (uint32_t)g.KS);
+                                }
+                                bt += tap16;
                             }
-                            b16 += g.tap_bytes >> 4;
+                            if (!g.b_resident) tc_commit(bar_b_empty + 8 * bs);
                         }
-                        if (!g.b_resident) tc_commit(bar_b_empty + 8 * bs);
+                        __syncwarp();
+                        nmma += (uint32_t)(g.TG * kmma);
+                        t += g.TG;
                         if (++bs == g.nb_stages) { bs = 0; bph ^= 1; }
                     }
-                    tc_commit(bar_a_empty + 8 * as);
+                    if (elect_one()) tc_commit(bar_a_empty + 8 * as);
+                    __syncwarp();
                     if (++as == g.na_stages) { as = 0; aph ^= 1; }
                 }
-                tc_commit(bar_acc_full + 8 * cs);
+                if (elect_one()) tc_commit(bar_acc_full + 8 * cs);
+                __syncwarp();
                 if (++cs == g.acc_stages) { cs = 0; cph ^= 1; }
             }
         }

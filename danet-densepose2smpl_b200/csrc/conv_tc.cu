@@ -34,10 +34,11 @@ namespace danet {
 namespace tc {
 
 constexpr int kTileH = 16, kTileW = 8;
-constexpr int kThreads = 448;            // warps 0-7: A producers, warps 8-11: epilogue, warp 12: B producer, warp 13: MMA + TMEM alloc
+constexpr int kThreads = 576;            // warps 0-7: A producers, warps 8-15: epilogue, warp 16: B producer, warp 17: MMA + TMEM alloc
 // (the issue arbiter favours the highest warp id of a scheduler: the single MMA-issuing thread
 //  must not sit behind 12 warps that poll mbarriers -- measured 370 cycles/MMA when it did)
-constexpr int kWarpEpi = 8, kWarpB = 12, kWarpMma = 13;
+constexpr int kWarpEpi = 8, kWarpB = 16, kWarpMma = 17;
+constexpr int kNumEpi = 256;             // two epilogue warps per TMEM lane quarter, each takes every other 16-column group
 constexpr int kNumProducers = 256;
 constexpr int kMaxBStages = 16;
 constexpr int kSmemBudget = 200 * 1024;  // one CTA per SM
@@ -252,7 +253,7 @@ k_conv_tc(const Args a) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full + 8 * i, 1); mbar_init(bar_acc_empty + 8 * i, 128); }   // stage 1 unused when acc_stages == 1
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full + 8 * i, 1); mbar_init(bar_acc_empty + 8 * i, kNumEpi); }   // stage 1 unused when acc_stages == 1
         for (int i = 0; i < g.na_stages; ++i) { mbar_init(bar_a_full + 8 * i, kNumProducers); mbar_init(bar_a_empty + 8 * i, 1); }
         for (int i = 0; i < g.nb_stages; ++i) { mbar_init(bar_b_full + 8 * i, 1); mbar_init(bar_b_empty + 8 * i, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -315,7 +316,7 @@ k_conv_tc(const Args a) {
             for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
                 mbar_wait(bar_acc_empty + 8 * cs, cph ^ 1);
                 tc_fence_after();
-                const uint32_t d_base = tmem_base + cs * (g.KS * g.NT);
+                const uint32_t d_base = tmem_base + cs * g.NT;
                 uint32_t nmma = 0;
                 for (int c = 0; c < g.nchunks; ++c) {
                     mbar_wait(bar_a_full + 8 * as, aph);
@@ -335,7 +336,7 @@ k_conv_tc(const Args a) {
                                     const uint64_t ad = ad_hi | (uint64_t)(((a16 + 2 * j) & 0x3FFFu) | lo_fixed);
                                     const uint64_t bd = bd_hi | (uint64_t)(((bt + 2 * j) & 0x3FFFu) | lo_fixed);
                                     const uint32_t n = nmma + (uint32_t)(tt * kmma + j);
-                                    tc_mma_tf32(d_base + (n & (uint32_t)(g.KS - 1)) * g.NT, ad, bd, idesc, n >= (uint32_t)g.KS);
+                                    tc_mma_tf32(d_base, ad, bd, idesc, n > 0u);
                                 }
                                 bt += tap16;
                             }
@@ -403,11 +404,13 @@ k_conv_tc(const Args a) {
                 if (++as == g.na_stages) { as = 0; aph ^= 1; }
             }
         }
-    } else {
+    } else if (warp < kWarpB) {
         // ================= epilogue: TMEM -> bias/residual/ReLU -> global =================
-        const int q = warp & 3;                                  // TMEM lane quarter this warp may access (warps 8..11 -> 0,1,2,3)
+        const int q = warp & 3;                                  // TMEM lane quarter this warp may access
+        const int half = (warp - kWarpEpi) >> 2;                 // 0/1: which 16-column groups of the tile this warp owns
         const int m = q * 32 + lane;
         const int hh = m >> 3, ww = m & 7;
+        const int ngroups = g.NT / 16;
         int cs = 0; uint32_t cph = 0;
         for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
             const int nt = tile % g.ntn;
@@ -419,48 +422,45 @@ k_conv_tc(const Args a) {
             const bool valid = oh < g.Ho && ow < g.Wo;
             const size_t pix = ((size_t)img * g.Ho * g.Wo + (size_t)oh * g.Wo + ow) * g.Cout;
             const float* bias = a.bias ? a.bias + (size_t)(img % g.wsets) * g.Cout : nullptr;
-            mbar_wait_sleep(bar_acc_full + 8 * cs, cph);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cs * (g.KS * g.NT);
-            for (int c0 = 0; c0 < g.NT; c0 += 16) {
-                const int ch0 = nt * g.NT + c0;
-                float4 rr[4];
+            // operands of the first group are fetched BEFORE waiting for the accumulator, and those of
+            // group i+1 while group i is processed: the global-load latency leaves the critical path
+            float4 rr[4], bb[4];
+            auto fetch = [&](int grp, float4* rv, float4* bv) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    rr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const int ch = ch0 + 4 * j;
-                    if (a.res && valid && ch < g.Cout) rr[j] = __ldg(reinterpret_cast<const float4*>(a.res + pix + ch));
+                    rv[j] = make_float4(0.f, 0.f, 0.f, 0.f); bv[j] = rv[j];
+                    const int ch = nt * g.NT + grp * 16 + 4 * j;
+                    if (grp < ngroups && ch < g.Cout) {
+                        if (bias) bv[j] = __ldg(reinterpret_cast<const float4*>(bias + ch));
+                        if (a.res && valid) rv[j] = __ldg(reinterpret_cast<const float4*>(a.res + pix + ch));
+                    }
                 }
-                float v[4][16];
-                tc_ld16_nowait(taddr + c0, v[0]);
-                if (g.KS > 1) tc_ld16_nowait(taddr + g.NT + c0, v[1]);
-                if (g.KS > 2) { tc_ld16_nowait(taddr + 2 * g.NT + c0, v[2]); tc_ld16_nowait(taddr + 3 * g.NT + c0, v[3]); }
+            };
+            fetch(half, rr, bb);
+            mbar_wait_sleep(bar_acc_full + 8 * cs, cph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cs * g.NT;
+            for (int grp = half; grp < ngroups; grp += 2) {
+                float v[16];
+                tc_ld16_nowait(taddr + grp * 16, v);
+                float4 rn[4], bn[4];
+                fetch(grp + 2, rn, bn);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (g.KS > 1) {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) v[0][e] += v[1][e];
-                }
-                if (g.KS > 2) {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) v[0][e] += v[2][e] + v[3][e];
-                }
                 if (valid) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const int ch = ch0 + 4 * j;
+                        const int ch = nt * g.NT + grp * 16 + 4 * j;
                         if (ch < g.Cout) {
-                            float4 o = make_float4(v[0][4 * j], v[0][4 * j + 1], v[0][4 * j + 2], v[0][4 * j + 3]);
-                            if (bias) {
-                                const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + ch));
-                                o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-                            }
-                            o.x += rr[j].x; o.y += rr[j].y; o.z += rr[j].z; o.w += rr[j].w;
+                            float4 o = make_float4(v[4 * j] + bb[j].x + rr[j].x, v[4 * j + 1] + bb[j].y + rr[j].y,
+                                                   v[4 * j + 2] + bb[j].z + rr[j].z, v[4 * j + 3] + bb[j].w + rr[j].w);
                             if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
                             o.x = to_tf32(o.x); o.y = to_tf32(o.y); o.z = to_tf32(o.z); o.w = to_tf32(o.w);
                             *reinterpret_cast<float4*>(a.y + pix + ch) = o;
                         }
                     }
                 }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { rr[j] = rn[j]; bb[j] = bn[j]; }
             }
             tc_fence_before();
             mbar_arrive(bar_acc_empty + 8 * cs);

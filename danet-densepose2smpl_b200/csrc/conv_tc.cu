@@ -308,42 +308,57 @@ k_conv_tc(const Args a) {
             int as = 0, bs = 0, cs = 0; uint32_t aph = 0, bph = 0, cph = 0;
             const uint32_t sbo_a = g.stride * g.WP * g.SWB, sbo_b = 8 * g.SWB;
             const uint32_t ltype = g.SWB == 128 ? 2u : (g.SWB == 64 ? 4u : 6u);
-            const uint64_t ad_hi = make_desc(0, sbo_a, ltype, 0u) & 0xFFFFFFFF00000000ull;
-            const uint64_t bd_hi = make_desc(0, sbo_b, ltype, 0u) & 0xFFFFFFFF00000000ull;
-            const uint32_t lo_fixed = 1u << 16;
+            // 64-bit descriptors are advanced by plain adds on their address field (16-byte units):
+            // all shared-memory addresses are < 256 KB, so the 14-bit field never carries.
+            const uint64_t ad0 = make_desc(0, sbo_a, ltype, 0u);
+            const uint64_t bd0 = make_desc(0, sbo_b, ltype, 0u);
             const int kmma = g.KCH / 8;
             const uint32_t tap16 = g.tap_bytes >> 4;
+            bool first_tile = true;
             for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
                 mbar_wait(bar_acc_empty + 8 * cs, cph ^ 1);
                 tc_fence_after();
                 const uint32_t d_base = tmem_base + cs * g.NT;
-                uint32_t nmma = 0;
+                uint32_t acc = 0;
                 for (int c = 0; c < g.nchunks; ++c) {
                     mbar_wait(bar_a_full + 8 * as, aph);
                     fence_proxy_async();                      // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
                     tc_fence_after();
-                    const uint32_t a_st16 = (sA + as * g.a_stage_bytes) >> 4;
+                    const uint64_t ad_st = ad0 + ((sA + as * g.a_stage_bytes) >> 4);
                     int t = 0;
                     for (int tg = 0; tg < g.ntg; ++tg) {
-                        mbar_wait(bar_b_full + 8 * bs, g.b_resident ? 0u : bph);
-                        tc_fence_after();
-                        const uint32_t b16 = (sB + bs * g.b_stage_bytes) >> 4;
+                        if (!g.b_resident || first_tile) {
+                            mbar_wait(bar_b_full + 8 * bs, g.b_resident ? 0u : bph);
+                            tc_fence_after();
+                        }
+                        uint64_t bd = bd0 + ((sB + bs * g.b_stage_bytes) >> 4);
                         if (elect_one()) {
-                            uint32_t bt = b16;
-                            for (int tt = 0; tt < g.TG; ++tt) {
-                                const uint32_t a16 = a_st16 + s_tapoff[t + tt];
-                                for (int j = 0; j < kmma; ++j) {
-                                    const uint64_t ad = ad_hi | (uint64_t)(((a16 + 2 * j) & 0x3FFFu) | lo_fixed);
-                                    const uint64_t bd = bd_hi | (uint64_t)(((bt + 2 * j) & 0x3FFFu) | lo_fixed);
-                                    const uint32_t n = nmma + (uint32_t)(tt * kmma + j);
-                                    tc_mma_tf32(d_base, ad, bd, idesc, n > 0u);
+                            if (kmma == 4) {
+                                for (int tt = 0; tt < g.TG; ++tt) {
+                                    const uint64_t ad = ad_st + s_tapoff[t + tt];
+                                    tc_mma_tf32(d_base, ad, bd, idesc, acc);
+                                    tc_mma_tf32(d_base, ad + 2, bd + 2, idesc, 1u);
+                                    tc_mma_tf32(d_base, ad + 4, bd + 4, idesc, 1u);
+                                    tc_mma_tf32(d_base, ad + 6, bd + 6, idesc, 1u);
+                                    acc = 1; bd += tap16;
                                 }
-                                bt += tap16;
+                            } else if (kmma == 2) {
+                                for (int tt = 0; tt < g.TG; ++tt) {
+                                    const uint64_t ad = ad_st + s_tapoff[t + tt];
+                                    tc_mma_tf32(d_base, ad, bd, idesc, acc);
+                                    tc_mma_tf32(d_base, ad + 2, bd + 2, idesc, 1u);
+                                    acc = 1; bd += tap16;
+                                }
+                            } else {
+                                for (int tt = 0; tt < g.TG; ++tt) {
+                                    tc_mma_tf32(d_base, ad_st + s_tapoff[t + tt], bd, idesc, acc);
+                                    acc = 1; bd += tap16;
+                                }
                             }
                             if (!g.b_resident) tc_commit(bar_b_empty + 8 * bs);
                         }
                         __syncwarp();
-                        nmma += (uint32_t)(g.TG * kmma);
+                        acc = 1;
                         t += g.TG;
                         if (++bs == g.nb_stages) { bs = 0; bph ^= 1; }
                     }
@@ -354,6 +369,7 @@ k_conv_tc(const Args a) {
                 if (elect_one()) tc_commit(bar_acc_full + 8 * cs);
                 __syncwarp();
                 if (++cs == g.acc_stages) { cs = 0; cph ^= 1; }
+                first_tile = false;
             }
         }
     } else if (warp < kWarpEpi) {

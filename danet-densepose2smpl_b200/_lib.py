@@ -61,6 +61,7 @@ SIGNATURES = {
     "danet_conv_tc_packed_bytes": (c_i64, [ctypes.POINTER(ConvDesc)]),
     "danet_conv_tc_pack": (c_int, [ctypes.POINTER(ConvDesc), c_p, c_p, c_p]),
     "danet_conv_tc_supported": (c_int, [ctypes.POINTER(ConvDesc)]),
+    "danet_conv_tc_set_profile_buffer": (c_int, [c_p]),
     "danet_nchw_to_nhwc": (c_int, [c_int, c_int, c_int, c_int, c_p, c_p, c_p]),
     "danet_fuse_sum": (c_int, [c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_int, c_p, c_p]),
     "danet_maxpool3x3s2": (c_int, [c_int, c_int, c_int, c_int, c_p, c_p, c_p]),

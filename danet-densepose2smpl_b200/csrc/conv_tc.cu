@@ -230,9 +230,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes
 // physical offset of logical byte offset `off` inside a 1024-byte-aligned swizzled tile
 __device__ __forceinline__ uint32_t swz(uint32_t off, uint32_t mask) { return off ^ (((off >> 7) & mask) << 4); }
 
+#define TC_PROF_BEGIN() long long _t0 = prof_on ? clock64() : 0
+#define TC_PROF_END(slot) do { if (prof_on) prof_acc[slot] += clock64() - _t0; } while (0)
+
 struct Args {
     Geom g;
     const float* x; const float* wpk; const float* bias; const float* res; float* y;
+    long long* prof;      // optional [16] cycle counters of CTA 0 (bring-up instrumentation), else NULL
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -315,21 +319,27 @@ k_conv_tc(const Args a) {
             const int kmma = g.KCH / 8;
             const uint32_t tap16 = g.tap_bytes >> 4;
             bool first_tile = true;
+            const bool prof_on = a.prof != nullptr && blockIdx.x == 0;
+            long long prof_acc[4] = {0, 0, 0, 0};
+            const long long t_start = prof_on ? clock64() : 0;
             for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
-                mbar_wait(bar_acc_empty + 8 * cs, cph ^ 1);
+                { TC_PROF_BEGIN(); mbar_wait(bar_acc_empty + 8 * cs, cph ^ 1); TC_PROF_END(0); }
+                if (false) mbar_wait(bar_acc_empty + 8 * cs, cph ^ 1);
                 tc_fence_after();
                 const uint32_t d_base = tmem_base + cs * g.NT;
                 uint32_t acc = 0;
                 for (int c = 0; c < g.nchunks; ++c) {
-                    mbar_wait(bar_a_full + 8 * as, aph);
+                    { TC_PROF_BEGIN(); mbar_wait(bar_a_full + 8 * as, aph); TC_PROF_END(1); }
                     fence_proxy_async();                      // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
                     tc_fence_after();
                     const uint64_t ad_st = ad0 + ((sA + as * g.a_stage_bytes) >> 4);
                     int t = 0;
                     for (int tg = 0; tg < g.ntg; ++tg) {
                         if (!g.b_resident || first_tile) {
+                            TC_PROF_BEGIN();
                             mbar_wait(bar_b_full + 8 * bs, g.b_resident ? 0u : bph);
                             tc_fence_after();
+                            TC_PROF_END(2);
                         }
                         uint64_t bd = bd0 + ((sB + bs * g.b_stage_bytes) >> 4);
                         if (elect_one()) {
@@ -371,6 +381,9 @@ k_conv_tc(const Args a) {
                 if (++cs == g.acc_stages) { cs = 0; cph ^= 1; }
                 first_tile = false;
             }
+            if (prof_on && lane == 0) {
+                a.prof[0] = clock64() - t_start; a.prof[1] = prof_acc[0]; a.prof[2] = prof_acc[1]; a.prof[3] = prof_acc[2];
+            }
         }
     } else if (warp < kWarpEpi) {
         // ================= A producers: halo tile -> smem (no-swizzle K-major) =================
@@ -387,6 +400,9 @@ k_conv_tc(const Args a) {
         const int sshift = g.stride - 1;                         // stride 1 -> 0, stride 2 -> 1
         const uint32_t smask = g.SWB == 128 ? 7u : (g.SWB == 64 ? 3u : 1u);
         int as = 0; uint32_t aph = 0;
+        const bool prof_on = a.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+        long long prof_acc[1] = {0};
+        const long long t_start = prof_on ? clock64() : 0;
         for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
             int r = tile / g.ntn;
             const int tw = r % g.tiles_w; r /= g.tiles_w;
@@ -395,7 +411,7 @@ k_conv_tc(const Args a) {
             const int h0 = th * kTileH * g.stride - g.pad, w0 = tw * kTileW * g.stride - g.pad;
             const float* xi = a.x + (size_t)img * HWC * g.Cin + cg * 4;
             for (int c = 0; c < g.nchunks; ++c) {
-                mbar_wait_sleep(bar_a_empty + 8 * as, aph ^ 1);
+                { TC_PROF_BEGIN(); mbar_wait_sleep(bar_a_empty + 8 * as, aph ^ 1); TC_PROF_END(0); }
                 const uint32_t a_st = sA + as * g.a_stage_bytes;
                 const bool ch_ok = c * g.KCH + cg * 4 < g.Cin;       // channels beyond Cin are zero-filled in smem
                 const float* xc = xi + c * g.KCH;
@@ -420,6 +436,7 @@ k_conv_tc(const Args a) {
                 if (++as == g.na_stages) { as = 0; aph ^= 1; }
             }
         }
+        if (prof_on) { a.prof[4] = clock64() - t_start; a.prof[5] = prof_acc[0]; }
     } else if (warp < kWarpB) {
         // ================= epilogue: TMEM -> bias/residual/ReLU -> global =================
         const int q = warp & 3;                                  // TMEM lane quarter this warp may access
@@ -428,6 +445,9 @@ k_conv_tc(const Args a) {
         const int hh = m >> 3, ww = m & 7;
         const int ngroups = g.NT / 16;
         int cs = 0; uint32_t cph = 0;
+        const bool prof_on = a.prof != nullptr && blockIdx.x == 0 && warp == kWarpEpi && lane == 0;
+        long long prof_acc[1] = {0};
+        const long long t_start = prof_on ? clock64() : 0;
         for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
             const int nt = tile % g.ntn;
             int r = tile / g.ntn;
@@ -453,7 +473,7 @@ k_conv_tc(const Args a) {
                 }
             };
             fetch(half, rr, bb);
-            mbar_wait_sleep(bar_acc_full + 8 * cs, cph);
+            { TC_PROF_BEGIN(); mbar_wait_sleep(bar_acc_full + 8 * cs, cph); TC_PROF_END(0); }
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cs * g.NT;
             for (int grp = half; grp < ngroups; grp += 2) {
@@ -482,6 +502,7 @@ k_conv_tc(const Args a) {
             mbar_arrive(bar_acc_empty + 8 * cs);
             if (++cs == g.acc_stages) { cs = 0; cph ^= 1; }
         }
+        if (prof_on) { a.prof[6] = clock64() - t_start; a.prof[7] = prof_acc[0]; }
     }
     tc_fence_before();
     __syncthreads();
@@ -521,11 +542,14 @@ __global__ void k_pack(const Geom g, const float* __restrict__ w, float* __restr
 
 }  // namespace tc
 
+static long long* g_tc_prof = nullptr;
+
 int conv_tc_launch(const danet_conv_desc* d, const float* x, const void* w_packed, const float* bias,
                    const float* residual, float* y, cudaStream_t stream) {
     tc::Args a;
     if (!tc::make_geom(d, &a.g)) { set_error("conv_tc_launch: unsupported shape"); return -1; }
     a.x = x; a.wpk = (const float*)w_packed; a.bias = bias; a.res = residual; a.y = y;
+    a.prof = g_tc_prof;
     static int sm_count = 0;
     static bool attr_set = false;
     if (!attr_set) {
@@ -546,6 +570,12 @@ int conv_tc_launch(const danet_conv_desc* d, const float* x, const void* w_packe
 }  // namespace danet
 
 using namespace danet;
+
+// bring-up instrumentation: device buffer of 16 int64 cycle counters written by CTA 0 of every
+// subsequent tcgen05 conv launch ([0] MMA warp total, [1] wait acc_empty, [2] wait A_full,
+// [3] wait B_full, [4] producer total, [5] producer wait A_empty, [6] epilogue total,
+// [7] epilogue wait acc_full); NULL disables it
+extern "C" int danet_conv_tc_set_profile_buffer(void* dev_buf) { g_tc_prof = (long long*)dev_buf; return 0; }
 
 extern "C" int danet_conv_tc_supported(const danet_conv_desc* d) {
     tc::Geom g;

@@ -140,6 +140,9 @@ int danet_conv2d(const danet_conv_desc* d, int32_t algo, const float* x, const f
 int64_t danet_conv_tc_packed_bytes(const danet_conv_desc* d);
 int danet_conv_tc_pack(const danet_conv_desc* d, const float* w_simt, void* w_packed, danet_stream_t stream);
 int danet_conv_tc_supported(const danet_conv_desc* d);
+/* bring-up instrumentation: 16 x int64 device buffer receiving per-role cycle counters of CTA 0 of
+ * every following tensor-core launch (NULL = off) */
+int danet_conv_tc_set_profile_buffer(void* dev_buf);
 
 /* input boundary: x NCHW [N,C,HW] -> y NHWC [N,HW,Cp] with Cp >= C zero-padded channels
  * (images arrive NCHW: demo.py:106, eval.py:147) */

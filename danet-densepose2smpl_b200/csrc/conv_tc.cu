@@ -1,4 +1,5 @@
-// tcgen05 TF32 implicit-GEMM convolution for sm_100a (1x1 / 3x3 / 7x7, stride 1 or 2, NHWC fp32).
+// tcgen05 implicit-GEMM convolution for sm_100a (1x1 / 3x3 / 7x7, stride 1 or 2, NHWC fp32 activations,
+// fp16 tensor-core operands converted on the fly, fp32 accumulation in TMEM).
 // The fast path of models/module/hr_module.py + res_module.py convolutions (conv + folded BN +
 // residual + ReLU); everything it does not take goes through csrc/conv_simt.cu.
 //
@@ -6,11 +7,9 @@
 //   M tile  = 128 output pixels = 16 rows x 8 columns of one image; N tile = up to 256 output
 //             channels; accumulators live in TMEM (double-buffered).
 //   A (activations): the input HALO of the tile ((15*s+k) x (7*s+k) pixels) is loaded ONCE per
-//             channel chunk by 8 producer warps (16-byte cp.async with zero fill, completion signalled
-//             by cp.async.mbarrier.arrive.noinc -- the producers never block on their own loads; the
-//             tensor core truncates fp32 to TF32, so every TC epilogue stores RN-rounded TF32 values
-//             and the next layer's operands are exact) into a SWIZZLED K-major UMMA layout: one row per halo pixel,
-//             SWB = 128/64/32 bytes (32/16/8 channels) per row, 16-byte chunks XOR-swizzled by the
+//             channel chunk by 8 producer warps (batched 16-byte global loads of the fp32 activations,
+//             RN conversion to fp16, 16-byte st.shared) into a SWIZZLED K-major UMMA layout: one row per halo pixel,
+//             SWB = 128/64/32 bytes (64/32/16 fp16 channels) per row, 16-byte chunks XOR-swizzled by the
 //             row phase exactly like TMA's SWIZZLE_128B/64B/32B, halo rows padded to a pitch of
 //             WP = 8k pixels so that every 8-row MMA group starts at the same swizzle phase.
 //             Eight consecutive MMA rows are eight consecutive pixels of one halo row; the next
@@ -23,12 +22,13 @@
 //   B (weights): pre-packed once (danet_conv_tc_pack) into the exact swizzled smem image of every
 //             (N tile, channel chunk, tap group) block, streamed by 1-D cp.async.bulk copies that
 //             complete on an mbarrier (no cuTensorMap); small weight sets stay resident in smem.
-//   MMA     : one elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N, K=8) and
+//   MMA     : one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N, K=16) and
 //             releases smem stages / publishes accumulators with tcgen05.commit -> mbarrier.
 //   Epilogue: 4 warps read TMEM with tcgen05.ld (32 lanes x 16 columns), add bias (+ residual),
 //             ReLU, and store 16-byte vectors to NHWC global memory.
 // Every mbarrier wait is bounded (traps instead of hanging the device).
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace danet {
 namespace tc {
@@ -49,7 +49,7 @@ struct Geom {
     int N, H, W, Cin, Cout, ks, pad, stride, relu, wsets;
     int Ho, Wo;
     int Wh, Hh, WP, plane_rows;          // halo: Hh x Wh input pixels; per column-parity plane Hh rows of WP pixels
-    int SWB, KCH, nchunks, CGT;          // swizzle bytes per row, channels per chunk (SWB/4), ceil(Cin/KCH), 16B chunks per row
+    int SWB, KCH, nchunks, CGT;          // swizzle bytes per row, channels per chunk (SWB/2, fp16), ceil(Cin/KCH), 16B chunks per row
     int TG, ntg;                         // filter taps per B stage, tap groups
     int NT, ntn;
     int tiles_w, tiles_h, total_tiles;
@@ -96,8 +96,8 @@ static bool make_geom(const danet_conv_desc* d, Geom* g) {
     // widest swizzle whose double-buffered halo + a minimal weight pipeline fits
     bool ok = false;
     for (int swb = 128; swb >= 32 && !ok; swb /= 2) {
-        if (swb / 4 > ((d->Cin + 7) / 8 * 8) && swb > 32) continue;   // do not pad tiny channel counts to a wide row
-        g->SWB = swb; g->KCH = swb / 4; g->CGT = swb / 16;
+        if (swb / 2 >= 2 * ((d->Cin + 15) / 16 * 16) && swb > 32) continue;   // do not pad tiny channel counts 2x to a wide row
+        g->SWB = swb; g->KCH = swb / 2; g->CGT = swb / 16;      // fp16 operands: 8 channels per 16-byte chunk
         g->nchunks = (d->Cin + g->KCH - 1) / g->KCH;
         g->a_stage_bytes = d->stride * g->plane_rows * swb;
         g->tap_bytes = g->NT * swb;
@@ -109,7 +109,7 @@ static bool make_geom(const danet_conv_desc* d, Geom* g) {
         }
     }
     if (!ok) return false;
-    while (g->KS > 1 && g->nchunks * taps * (g->KCH / 8) < g->KS) g->KS /= 2;
+    while (g->KS > 1 && g->nchunks * taps * (g->KCH / 16) < g->KS) g->KS /= 2;
     const int nblk = g->nchunks * g->ntg;
     g->na_stages = 2;
     g->b_resident = 0; g->ctas_per_sm = 1;
@@ -186,7 +186,7 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uin
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
 __device__ __forceinline__ bool elect_one() {
@@ -214,6 +214,11 @@ __device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, float* v) {
         : "r"(taddr) : "memory");
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));   // d = {hi -> upper, lo -> lower}
+    return r;
 }
 __device__ __forceinline__ float to_tf32(float x) {
     uint32_t r;
@@ -308,7 +313,8 @@ k_conv_tc(const Args a) {
         // region made ptxas wrap every UTCHMMA in an ELECT/BRA.U.ANY loop: ~30 SASS instructions
         // and ~240 cycles per MMA (profiles/r01_ncu_conv_tc_v6_summary.txt).
         {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.NT >> 3) << 17) | ((128u >> 4) << 24);
+            // kind::f16, A/B = F16 (format 0), D = F32, both K-major, N>>3 at bit 17, M>>4 at bit 24
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(g.NT >> 3) << 17) | ((128u >> 4) << 24);
             int as = 0, bs = 0, cs = 0; uint32_t aph = 0, bph = 0, cph = 0;
             const uint32_t sbo_a = g.stride * g.WP * g.SWB, sbo_b = 8 * g.SWB;
             const uint32_t ltype = g.SWB == 128 ? 2u : (g.SWB == 64 ? 4u : 6u);
@@ -316,7 +322,7 @@ k_conv_tc(const Args a) {
             // all shared-memory addresses are < 256 KB, so the 14-bit field never carries.
             const uint64_t ad0 = make_desc(0, sbo_a, ltype, 0u);
             const uint64_t bd0 = make_desc(0, sbo_b, ltype, 0u);
-            const int kmma = g.KCH / 8;
+            const int kmma = g.KCH / 16;                         // K = 16 halves (32 bytes) per MMA
             const uint32_t tap16 = g.tap_bytes >> 4;
             bool first_tile = true;
             const bool prof_on = a.prof != nullptr && blockIdx.x == 0;
@@ -391,7 +397,7 @@ k_conv_tc(const Args a) {
         // halo coordinates are updated incrementally (no divisions in the loop); every pass's
         // global load is issued before the first shared store (one latency exposure per 8 passes).
         const int pt = threadIdx.x;                             // 0..255
-        const int cg = pt & (g.CGT - 1);                         // 16-byte chunk (4 channels) within the row
+        const int cg = pt & (g.CGT - 1);                         // 16-byte chunk (8 fp16 channels) within the row
         const int ppt = kNumProducers / g.CGT;                   // pixels per pass
         const int px0 = pt / g.CGT;
         const int hh0 = px0 / g.Wh, ww0 = px0 - hh0 * g.Wh;
@@ -409,30 +415,46 @@ k_conv_tc(const Args a) {
             const int th = r % g.tiles_h;
             const int img = r / g.tiles_h;
             const int h0 = th * kTileH * g.stride - g.pad, w0 = tw * kTileW * g.stride - g.pad;
-            const float* xi = a.x + (size_t)img * HWC * g.Cin + cg * 4;
+            const float* xi = a.x + (size_t)img * HWC * g.Cin + cg * 8;
             for (int c = 0; c < g.nchunks; ++c) {
                 { TC_PROF_BEGIN(); mbar_wait_sleep(bar_a_empty + 8 * as, aph ^ 1); TC_PROF_END(0); }
                 const uint32_t a_st = sA + as * g.a_stage_bytes;
-                const bool ch_ok = c * g.KCH + cg * 4 < g.Cin;       // channels beyond Cin are zero-filled in smem
+                const bool ch_ok = c * g.KCH + cg * 8 < g.Cin;       // channels beyond Cin are zero-filled in smem
                 const float* xc = xi + c * g.KCH;
                 int hh = hh0, ww = ww0;
-                // fully asynchronous: every 16-byte piece is a cp.async (zero-filled when it is padding or a
-                // channel beyond Cin); the stage barrier is armed with cp.async.mbarrier.arrive.noinc, so
-                // the producer never waits for its own loads and runs up to na_stages ahead of the MMAs.
-#pragma unroll 4
-                for (int p = 0; p < npass; ++p) {
-                    if (hh < g.Hh) {
-                        const int ih = h0 + hh, iw = w0 + ww;
-                        const uint32_t row = (ww & sshift) * g.plane_rows + hh * g.WP + (ww >> sshift);
-                        const uint32_t dst = a_st + swz(row * g.SWB + cg * 16, smask);
-                        const bool ok = ch_ok && ih >= 0 && ih < g.H && iw >= 0 && iw < g.W;
-                        const float* src = ok ? xc + ((size_t)ih * g.W + iw) * g.Cin : a.x;
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16u : 0u) : "memory");
+                // fp32 activations are converted to fp16 (RN, saturating) on the way into shared memory:
+                // half the operand bytes per MAC for the tensor core and twice the K per MMA.  All global
+                // loads of a batch are issued before the first conversion/store.
+                const bool ch_ok2 = c * g.KCH + cg * 8 + 4 < g.Cin;  // second float4 of the 8-channel chunk
+                for (int p0 = 0; p0 < npass; p0 += 6) {
+                    float4 v0[6], v1[6];
+                    uint32_t dst[6];
+#pragma unroll
+                    for (int u = 0; u < 6; ++u) {
+                        v0[u] = make_float4(0.f, 0.f, 0.f, 0.f); v1[u] = v0[u];
+                        dst[u] = 0xFFFFFFFFu;
+                        if (p0 + u < npass && hh < g.Hh) {
+                            const int ih = h0 + hh, iw = w0 + ww;
+                            const uint32_t row = (ww & sshift) * g.plane_rows + hh * g.WP + (ww >> sshift);
+                            dst[u] = a_st + swz(row * g.SWB + cg * 16, smask);
+                            if (ch_ok && ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) {
+                                const float4* src = reinterpret_cast<const float4*>(xc + ((size_t)ih * g.W + iw) * g.Cin);
+                                v0[u] = __ldg(src);
+                                if (ch_ok2) v1[u] = __ldg(src + 1);
+                            }
+                        }
+                        ww += dww; hh += dhh;
+                        if (ww >= g.Wh) { ww -= g.Wh; hh += 1; }
                     }
-                    ww += dww; hh += dhh;
-                    if (ww >= g.Wh) { ww -= g.Wh; hh += 1; }
+#pragma unroll
+                    for (int u = 0; u < 6; ++u) {
+                        if (dst[u] != 0xFFFFFFFFu)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst[u]), "r"(pack_h2(v0[u].x, v0[u].y)),
+                                         "r"(pack_h2(v0[u].z, v0[u].w)), "r"(pack_h2(v1[u].x, v1[u].y)), "r"(pack_h2(v1[u].z, v1[u].w)) : "memory");
+                    }
                 }
-                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_a_full + 8 * as) : "memory");
+                fence_proxy_async();
+                mbar_arrive(bar_a_full + 8 * as);
                 if (++as == g.na_stages) { as = 0; aph ^= 1; }
             }
         }
@@ -490,7 +512,6 @@ k_conv_tc(const Args a) {
                             float4 o = make_float4(v[4 * j] + bb[j].x + rr[j].x, v[4 * j + 1] + bb[j].y + rr[j].y,
                                                    v[4 * j + 2] + bb[j].z + rr[j].z, v[4 * j + 3] + bb[j].w + rr[j].w);
                             if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                            o.x = to_tf32(o.x); o.y = to_tf32(o.y); o.z = to_tf32(o.z); o.w = to_tf32(o.w);
                             *reinterpret_cast<float4*>(a.y + pix + ch) = o;
                         }
                     }
@@ -512,22 +533,22 @@ k_conv_tc(const Args a) {
     }
 }
 
-// weight packing: SIMT layout [wsets][ks*ks*Cin][Cout] -> swizzled smem-image blocks, TF32-rounded
+// weight packing: SIMT layout [wsets][ks*ks*Cin][Cout] fp32 -> swizzled smem-image blocks of fp16
 // block (ws, nt, chunk, tap group) = [TG taps][NT rows][SWB bytes], rows = output channels
-__global__ void k_pack(const Geom g, const float* __restrict__ w, float* __restrict__ out) {
-    const int blk_floats = g.b_stage_bytes / 4;
-    const long long total = (long long)g.wsets * g.blocks_per_set * blk_floats;
+__global__ void k_pack(const Geom g, const float* __restrict__ w, __half* __restrict__ out) {
+    const int blk_halves = g.b_stage_bytes / 2;
+    const long long total = (long long)g.wsets * g.blocks_per_set * blk_halves;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int taps = g.ks * g.ks;
-    long long blk = i / blk_floats;
-    const uint32_t poff = (uint32_t)(i % blk_floats) * 4;             // physical byte offset inside the block
+    long long blk = i / blk_halves;
+    const uint32_t poff = (uint32_t)(i % blk_halves) * 2;             // physical byte offset inside the block
     const int tt = poff / g.tap_bytes;
     float v = 0.f;
     if (tt < g.TG) {
         const uint32_t smask = g.SWB == 128 ? 7u : (g.SWB == 64 ? 3u : 1u);
         const uint32_t loff = swz(poff - tt * g.tap_bytes, smask);     // the XOR swizzle is an involution
-        const int n = loff / g.SWB, kk = (loff % g.SWB) / 4;
+        const int n = loff / g.SWB, kk = (loff % g.SWB) / 2;
         const int tgi = (int)(blk % g.ntg); blk /= g.ntg;
         const int c = (int)(blk % g.nchunks); blk /= g.nchunks;
         const int nt = (int)(blk % g.ntn);
@@ -537,7 +558,7 @@ __global__ void k_pack(const Geom g, const float* __restrict__ w, float* __restr
         const int co = nt * g.NT + n;
         if (co < g.Cout && cin < g.Cin) v = w[((size_t)ws * taps * g.Cin + (size_t)t * g.Cin + cin) * g.Cout + co];
     }
-    out[i] = to_tf32(v);
+    out[i] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
 }
 
 }  // namespace tc
@@ -592,8 +613,8 @@ extern "C" int danet_conv_tc_pack(const danet_conv_desc* d, const float* w_simt,
     tc::Geom g;
     DANET_CHECK(d && tc::make_geom(d, &g), "danet_conv_tc_pack: shape not supported by the tcgen05 path");
     DANET_CHECK(w_simt && w_packed, "danet_conv_tc_pack: null pointer");
-    const long long total = (long long)g.wsets * g.blocks_per_set * (g.b_stage_bytes / 4);
-    tc::k_pack<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g, w_simt, (float*)w_packed);
+    const long long total = (long long)g.wsets * g.blocks_per_set * (g.b_stage_bytes / 2);
+    tc::k_pack<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g, w_simt, (__half*)w_packed);
     DANET_LAUNCH_CHECK();
     return 0;
 }

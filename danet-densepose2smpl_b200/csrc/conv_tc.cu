@@ -48,9 +48,17 @@ constexpr bool kAllowTwoCtas = false;    // needs <= 73 registers/thread (curren
 struct Geom {
     int N, H, W, Cin, Cout, ks, pad, stride, relu, wsets;
     int Ho, Wo;
-    int Wh, Hh, WP, plane_rows;          // halo: Hh x Wh input pixels; per column-parity plane Hh rows of WP pixels
+    int WP, HPmax;                       // A stage = one parity plane of the halo: up to HPmax rows of WP pixels (WP % 8 == 0)
+    // stride-2 convolutions are decomposed by input parity (py,px): each parity plane is a dense
+    // stride-1 problem with its own subset of the filter taps, so every A stage uses the full-width
+    // swizzled layout.  Stride 1 = a single plane with all taps.
+    int npa;                             // active parity planes (1 for stride 1, up to 4 for stride 2)
+    int par_py[4], par_px[4], ntap[4], ngrp[4], blkoff[4], Hp[4], Wp[4];
+    int tapoff16[4][16];                 // smem offset (16-byte units) of each tap's shifted view inside the plane
+    int tapidx[4][16];                   // original filter tap index r*ks+s (for weight packing)
+    int bpc;                             // weight blocks per channel chunk = sum of ngrp
     int SWB, KCH, nchunks, CGT;          // swizzle bytes per row, channels per chunk (SWB/2, fp16), ceil(Cin/KCH), 16B chunks per row
-    int TG, ntg;                         // filter taps per B stage, tap groups
+    int TG;                              // filter taps per B stage (ragged last group per plane)
     int NT, ntn;
     int tiles_w, tiles_h, total_tiles;
     int a_stage_bytes, b_stage_bytes, tap_bytes, nb_stages, na_stages;
@@ -72,12 +80,27 @@ static bool make_geom(const danet_conv_desc* d, Geom* g) {
     g->N = d->N; g->H = d->H; g->W = d->W; g->Cin = d->Cin; g->Cout = d->Cout; g->ks = d->ksize;
     g->pad = d->pad; g->stride = d->stride; g->relu = d->relu; g->wsets = d->wsets;
     g->variant = tc_variant();
+    g->KS = 1; g->acc_stages = 2;
     g->Ho = (d->H + 2 * d->pad - d->ksize) / d->stride + 1;
     g->Wo = (d->W + 2 * d->pad - d->ksize) / d->stride + 1;
-    g->Wh = (kTileW - 1) * d->stride + d->ksize; g->Hh = (kTileH - 1) * d->stride + d->ksize;
-    const int wcols = (g->Wh + d->stride - 1) / d->stride;           // columns per parity plane
-    g->WP = (wcols + 7) / 8 * 8;
-    g->plane_rows = g->Hh * g->WP;
+    // parity decomposition
+    g->npa = 0;
+    int max_tr = 0, max_tc = 0, max_ntap = 0;
+    for (int py = 0; py < d->stride; ++py)
+        for (int px = 0; px < d->stride; ++px) {
+            const int tr = py < d->ksize ? (d->ksize - 1 - py) / d->stride + 1 : 0;     // taps r = py + stride*i
+            const int tcn = px < d->ksize ? (d->ksize - 1 - px) / d->stride + 1 : 0;
+            if (tr * tcn == 0) continue;
+            if (tr * tcn > 16) return false;
+            const int a = g->npa++;
+            g->par_py[a] = py; g->par_px[a] = px; g->ntap[a] = tr * tcn;
+            g->Hp[a] = kTileH + tr - 1; g->Wp[a] = kTileW + tcn - 1;
+            max_tr = tr > max_tr ? tr : max_tr; max_tc = tcn > max_tc ? tcn : max_tc;
+            max_ntap = tr * tcn > max_ntap ? tr * tcn : max_ntap;
+        }
+    for (int a = g->npa; a < 4; ++a) { g->par_py[a] = g->par_px[a] = g->ntap[a] = g->ngrp[a] = g->blkoff[a] = g->Hp[a] = g->Wp[a] = 0; }
+    g->HPmax = kTileH + max_tr - 1;
+    g->WP = (kTileW + max_tc - 1 + 7) / 8 * 8;
     const int np = (d->Cout + 15) / 16 * 16;
     g->ntn = (np + 255) / 256;
     g->NT = ((np + g->ntn - 1) / g->ntn + 15) / 16 * 16;
@@ -99,18 +122,30 @@ static bool make_geom(const danet_conv_desc* d, Geom* g) {
         if (swb / 2 >= 2 * ((d->Cin + 15) / 16 * 16) && swb > 32) continue;   // do not pad tiny channel counts 2x to a wide row
         g->SWB = swb; g->KCH = swb / 2; g->CGT = swb / 16;      // fp16 operands: 8 channels per 16-byte chunk
         g->nchunks = (d->Cin + g->KCH - 1) / g->KCH;
-        g->a_stage_bytes = d->stride * g->plane_rows * swb;
+        g->a_stage_bytes = g->HPmax * g->WP * swb;
         g->tap_bytes = g->NT * swb;
-        for (int t = taps; t >= 1 && !ok; --t) {
-            if (taps % t != 0 || (t > 1 && t * g->tap_bytes > 32 * 1024)) continue;
-            g->TG = t; g->ntg = taps / t;
+        for (int t = max_ntap; t >= 1 && !ok; --t) {
+            if (t > 1 && t * g->tap_bytes > 32 * 1024) continue;
+            g->TG = t;
             g->b_stage_bytes = (t * g->tap_bytes + 1023) / 1024 * 1024;
             if (2 * g->a_stage_bytes + 2 * g->b_stage_bytes + fixed <= kSmemBudget) ok = true;
         }
     }
     if (!ok) return false;
-    while (g->KS > 1 && g->nchunks * taps * (g->KCH / 16) < g->KS) g->KS /= 2;
-    const int nblk = g->nchunks * g->ntg;
+    g->bpc = 0;
+    for (int a = 0; a < g->npa; ++a) {
+        g->ngrp[a] = (g->ntap[a] + g->TG - 1) / g->TG;
+        g->blkoff[a] = g->bpc; g->bpc += g->ngrp[a];
+        const int tcn = g->Wp[a] - kTileW + 1;
+        for (int k = 0; k < 16; ++k) { g->tapoff16[a][k] = 0; g->tapidx[a][k] = 0; }
+        for (int k = 0; k < g->ntap[a]; ++k) {
+            const int ti = k / tcn, tj = k % tcn;
+            g->tapoff16[a][k] = ((ti * g->WP + tj) * g->SWB) >> 4;
+            g->tapidx[a][k] = (g->par_py[a] + d->stride * ti) * d->ksize + (g->par_px[a] + d->stride * tj);
+        }
+    }
+    (void)taps;
+    const int nblk = g->nchunks * g->bpc;
     g->na_stages = 2;
     g->b_resident = 0; g->ctas_per_sm = 1;
     if (d->wsets == 1 && g->ntn == 1 && nblk <= kMaxBStages &&
@@ -279,13 +314,6 @@ k_conv_tc(const Args a) {
 
     const int taps = g.ks * g.ks;
     const int HWC = g.H * g.W;
-    __shared__ uint32_t s_tapoff[49];
-    if (threadIdx.x < taps) {
-        const int t = threadIdx.x, fr = t / g.ks, fs = t - fr * g.ks;
-        s_tapoff[t] = (uint32_t)(((fs % g.stride) * g.plane_rows + fr * g.WP + fs / g.stride) * g.SWB) >> 4;
-    }
-    __syncthreads();
-
     if (warp == kWarpB) {
         // ================= B producer: bulk copies of pre-packed weight blocks =================
         if (lane == 0) {
@@ -295,8 +323,8 @@ k_conv_tc(const Args a) {
                 const int img = tile / (g.ntn * g.tiles_w * g.tiles_h);
                 const int ws = img % g.wsets;
                 const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wpk) +
-                    ((long long)ws * g.blocks_per_set + (long long)nt * g.nchunks * g.ntg) * g.b_stage_bytes;
-                const int nblk = g.nchunks * g.ntg;
+                    ((long long)ws * g.blocks_per_set + (long long)nt * g.nchunks * g.bpc) * g.b_stage_bytes;
+                const int nblk = g.nchunks * g.bpc;
                 if (g.b_resident && tile != (int)blockIdx.x) break;          // weights already resident
                 for (int b = 0; b < nblk; ++b) {
                     if (!g.b_resident) mbar_wait_sleep(bar_b_empty + 8 * bs, bph ^ 1);
@@ -316,7 +344,7 @@ k_conv_tc(const Args a) {
             // kind::f16, A/B = F16 (format 0), D = F32, both K-major, N>>3 at bit 17, M>>4 at bit 24
             const uint32_t idesc = (1u << 4) | ((uint32_t)(g.NT >> 3) << 17) | ((128u >> 4) << 24);
             int as = 0, bs = 0, cs = 0; uint32_t aph = 0, bph = 0, cph = 0;
-            const uint32_t sbo_a = g.stride * g.WP * g.SWB, sbo_b = 8 * g.SWB;
+            const uint32_t sbo_a = g.WP * g.SWB, sbo_b = 8 * g.SWB;
             const uint32_t ltype = g.SWB == 128 ? 2u : (g.SWB == 64 ? 4u : 6u);
             // 64-bit descriptors are advanced by plain adds on their address field (16-byte units):
             // all shared-memory addresses are < 256 KB, so the 14-bit field never carries.
@@ -334,13 +362,13 @@ k_conv_tc(const Args a) {
                 tc_fence_after();
                 const uint32_t d_base = tmem_base + cs * g.NT;
                 uint32_t acc = 0;
-                for (int c = 0; c < g.nchunks; ++c) {
+                for (int u = 0; u < g.nchunks * g.npa; ++u) {
+                    const int slot = u % g.npa;
                     { TC_PROF_BEGIN(); mbar_wait(bar_a_full + 8 * as, aph); TC_PROF_END(1); }
-                    fence_proxy_async();                      // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
+                    fence_proxy_async();
                     tc_fence_after();
                     const uint64_t ad_st = ad0 + ((sA + as * g.a_stage_bytes) >> 4);
-                    int t = 0;
-                    for (int tg = 0; tg < g.ntg; ++tg) {
+                    for (int tg = 0; tg < g.ngrp[slot]; ++tg) {
                         if (!g.b_resident || first_tile) {
                             TC_PROF_BEGIN();
                             mbar_wait(bar_b_full + 8 * bs, g.b_resident ? 0u : bph);
@@ -348,10 +376,12 @@ k_conv_tc(const Args a) {
                             TC_PROF_END(2);
                         }
                         uint64_t bd = bd0 + ((sB + bs * g.b_stage_bytes) >> 4);
+                        const int k0 = tg * g.TG;
+                        const int ntk = min(g.TG, g.ntap[slot] - k0);
                         if (elect_one()) {
                             if (kmma == 4) {
-                                for (int tt = 0; tt < g.TG; ++tt) {
-                                    const uint64_t ad = ad_st + s_tapoff[t + tt];
+                                for (int tt = 0; tt < ntk; ++tt) {
+                                    const uint64_t ad = ad_st + (uint32_t)g.tapoff16[slot][k0 + tt];
                                     tc_mma_tf32(d_base, ad, bd, idesc, acc);
                                     tc_mma_tf32(d_base, ad + 2, bd + 2, idesc, 1u);
                                     tc_mma_tf32(d_base, ad + 4, bd + 4, idesc, 1u);
@@ -359,15 +389,15 @@ k_conv_tc(const Args a) {
                                     acc = 1; bd += tap16;
                                 }
                             } else if (kmma == 2) {
-                                for (int tt = 0; tt < g.TG; ++tt) {
-                                    const uint64_t ad = ad_st + s_tapoff[t + tt];
+                                for (int tt = 0; tt < ntk; ++tt) {
+                                    const uint64_t ad = ad_st + (uint32_t)g.tapoff16[slot][k0 + tt];
                                     tc_mma_tf32(d_base, ad, bd, idesc, acc);
                                     tc_mma_tf32(d_base, ad + 2, bd + 2, idesc, 1u);
                                     acc = 1; bd += tap16;
                                 }
                             } else {
-                                for (int tt = 0; tt < g.TG; ++tt) {
-                                    tc_mma_tf32(d_base, ad_st + s_tapoff[t + tt], bd, idesc, acc);
+                                for (int tt = 0; tt < ntk; ++tt) {
+                                    tc_mma_tf32(d_base, ad_st + (uint32_t)g.tapoff16[slot][k0 + tt], bd, idesc, acc);
                                     acc = 1; bd += tap16;
                                 }
                             }
@@ -375,7 +405,6 @@ k_conv_tc(const Args a) {
                         }
                         __syncwarp();
                         acc = 1;
-                        t += g.TG;
                         if (++bs == g.nb_stages) { bs = 0; bph ^= 1; }
                     }
                     if (elect_one()) tc_commit(bar_a_empty + 8 * as);
@@ -400,10 +429,6 @@ k_conv_tc(const Args a) {
         const int cg = pt & (g.CGT - 1);                         // 16-byte chunk (8 fp16 channels) within the row
         const int ppt = kNumProducers / g.CGT;                   // pixels per pass
         const int px0 = pt / g.CGT;
-        const int hh0 = px0 / g.Wh, ww0 = px0 - hh0 * g.Wh;
-        const int dhh = ppt / g.Wh, dww = ppt - dhh * g.Wh;
-        const int npass = (g.Hh * g.Wh + ppt - 1) / ppt;
-        const int sshift = g.stride - 1;                         // stride 1 -> 0, stride 2 -> 1
         const uint32_t smask = g.SWB == 128 ? 7u : (g.SWB == 64 ? 3u : 1u);
         int as = 0; uint32_t aph = 0;
         const bool prof_on = a.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
@@ -416,41 +441,45 @@ k_conv_tc(const Args a) {
             const int img = r / g.tiles_h;
             const int h0 = th * kTileH * g.stride - g.pad, w0 = tw * kTileW * g.stride - g.pad;
             const float* xi = a.x + (size_t)img * HWC * g.Cin + cg * 8;
-            for (int c = 0; c < g.nchunks; ++c) {
+            for (int u = 0; u < g.nchunks * g.npa; ++u) {
+                const int c = u / g.npa, slot = u - c * g.npa;
+                const int Wp = g.Wp[slot], Hp = g.Hp[slot];
+                const int hb = h0 + g.par_py[slot], wb = w0 + g.par_px[slot];
+                const int npass = (Hp * Wp + ppt - 1) / ppt;
+                const int dhh = ppt / Wp, dww = ppt - dhh * Wp;
+                int hh = px0 / Wp, ww = px0 - hh * Wp;
                 { TC_PROF_BEGIN(); mbar_wait_sleep(bar_a_empty + 8 * as, aph ^ 1); TC_PROF_END(0); }
                 const uint32_t a_st = sA + as * g.a_stage_bytes;
                 const bool ch_ok = c * g.KCH + cg * 8 < g.Cin;       // channels beyond Cin are zero-filled in smem
+                const bool ch_ok2 = c * g.KCH + cg * 8 + 4 < g.Cin;  // second float4 of the 8-channel chunk
                 const float* xc = xi + c * g.KCH;
-                int hh = hh0, ww = ww0;
                 // fp32 activations are converted to fp16 (RN, saturating) on the way into shared memory:
                 // half the operand bytes per MAC for the tensor core and twice the K per MMA.  All global
                 // loads of a batch are issued before the first conversion/store.
-                const bool ch_ok2 = c * g.KCH + cg * 8 + 4 < g.Cin;  // second float4 of the 8-channel chunk
                 for (int p0 = 0; p0 < npass; p0 += 6) {
                     float4 v0[6], v1[6];
                     uint32_t dst[6];
 #pragma unroll
-                    for (int u = 0; u < 6; ++u) {
-                        v0[u] = make_float4(0.f, 0.f, 0.f, 0.f); v1[u] = v0[u];
-                        dst[u] = 0xFFFFFFFFu;
-                        if (p0 + u < npass && hh < g.Hh) {
-                            const int ih = h0 + hh, iw = w0 + ww;
-                            const uint32_t row = (ww & sshift) * g.plane_rows + hh * g.WP + (ww >> sshift);
-                            dst[u] = a_st + swz(row * g.SWB + cg * 16, smask);
+                    for (int q = 0; q < 6; ++q) {
+                        v0[q] = make_float4(0.f, 0.f, 0.f, 0.f); v1[q] = v0[q];
+                        dst[q] = 0xFFFFFFFFu;
+                        if (p0 + q < npass && hh < Hp) {
+                            const int ih = hb + g.stride * hh, iw = wb + g.stride * ww;
+                            dst[q] = a_st + swz((uint32_t)(hh * g.WP + ww) * g.SWB + cg * 16, smask);
                             if (ch_ok && ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) {
                                 const float4* src = reinterpret_cast<const float4*>(xc + ((size_t)ih * g.W + iw) * g.Cin);
-                                v0[u] = __ldg(src);
-                                if (ch_ok2) v1[u] = __ldg(src + 1);
+                                v0[q] = __ldg(src);
+                                if (ch_ok2) v1[q] = __ldg(src + 1);
                             }
                         }
                         ww += dww; hh += dhh;
-                        if (ww >= g.Wh) { ww -= g.Wh; hh += 1; }
+                        if (ww >= Wp) { ww -= Wp; hh += 1; }
                     }
 #pragma unroll
-                    for (int u = 0; u < 6; ++u) {
-                        if (dst[u] != 0xFFFFFFFFu)
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst[u]), "r"(pack_h2(v0[u].x, v0[u].y)),
-                                         "r"(pack_h2(v0[u].z, v0[u].w)), "r"(pack_h2(v1[u].x, v1[u].y)), "r"(pack_h2(v1[u].z, v1[u].w)) : "memory");
+                    for (int q = 0; q < 6; ++q) {
+                        if (dst[q] != 0xFFFFFFFFu)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst[q]), "r"(pack_h2(v0[q].x, v0[q].y)),
+                                         "r"(pack_h2(v0[q].z, v0[q].w)), "r"(pack_h2(v1[q].x, v1[q].y)), "r"(pack_h2(v1[q].z, v1[q].w)) : "memory");
                     }
                 }
                 fence_proxy_async();
@@ -549,11 +578,16 @@ __global__ void k_pack(const Geom g, const float* __restrict__ w, __half* __rest
         const uint32_t smask = g.SWB == 128 ? 7u : (g.SWB == 64 ? 3u : 1u);
         const uint32_t loff = swz(poff - tt * g.tap_bytes, smask);     // the XOR swizzle is an involution
         const int n = loff / g.SWB, kk = (loff % g.SWB) / 2;
-        const int tgi = (int)(blk % g.ntg); blk /= g.ntg;
+        int bi = (int)(blk % g.bpc); blk /= g.bpc;
+        int slot = 0;
+        while (slot + 1 < g.npa && bi >= g.blkoff[slot + 1]) ++slot;
+        const int tgi = bi - g.blkoff[slot];
         const int c = (int)(blk % g.nchunks); blk /= g.nchunks;
         const int nt = (int)(blk % g.ntn);
         const int ws = (int)(blk / g.ntn);
-        const int t = tgi * g.TG + tt;
+        const int k = tgi * g.TG + tt;
+        if (k >= g.ntap[slot]) { out[i] = __float2half_rn(0.f); return; }
+        const int t = g.tapidx[slot][k];
         const int cin = c * g.KCH + kk;
         const int co = nt * g.NT + n;
         if (co < g.Cout && cin < g.Cin) v = w[((size_t)ws * taps * g.Cin + (size_t)t * g.Cin + cin) * g.Cout + co];

@@ -263,11 +263,20 @@ def run_b200_arm(args):
         conv_ms = prof["conv_ms"]
         flops = FLOP_PER_IMG.get(W, 0.0) * B
         conv_tflops = flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
-        tf32_peak = pk["bf16_tflops_sustained"] / 2.0
-        roof = {"bound": "tensor", "kernel": prof["conv_kernel"], "achieved": conv_tflops, "peak": tf32_peak,
-                "unit": "TFLOP/s", "frac": conv_tflops / tf32_peak if tf32_peak else None, "traffic": None,
-                "peak_note": "TF32 dense = half of the %s bf16 sustained cuBLAS figure (%.0f TFLOP/s); fp32-FMA "
-                             "launches are rated against the same denominator" % (pk["source"], pk["bf16_tflops_sustained"]),
+        tc_peak = pk["bf16_tflops_sustained"]
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "conv_traffic.json")
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            if tj.get("width") == W and tj.get("batch") == B:
+                traffic, traffic_src = tj.get("dram_bytes_per_step"), tj.get("source")
+        roof = {"bound": "tensor", "kernel": prof["conv_kernel"], "achieved": conv_tflops, "peak": tc_peak,
+                "unit": "TFLOP/s", "frac": conv_tflops / tc_peak if tc_peak else None, "traffic": traffic,
+                "traffic_note": traffic_src,
+                "peak_note": "16-bit dense tensor peak = the %s sustained cuBLAS bf16 figure (%.0f TFLOP/s; kernel timed "
+                             "inside a long step); achieved = algorithmic conv FLOPs of one step / summed duration of "
+                             "its conv launches (CUDA events per launch); the few fp32-FMA launches are rated against "
+                             "the same denominator" % (pk["source"], pk["bf16_tflops_sustained"]),
                 "algorithmic_flop_per_launch_group": flops, "conv_ms_per_step": conv_ms,
                 "conv_share_of_step": conv_ms / (ms / args.steps), "n_conv_tc": plan.n_tc,
                 "n_conv_total": prof["n_conv"], "other_ms": prof["other_ms"]}
@@ -278,10 +287,10 @@ def run_b200_arm(args):
         line = {"metric": "images/sec DaNet fwd bs=%d 224x224 (HRNet-W%d + part regressors + SMPL LBS + IUV render)" % (B, W),
                 "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "tf32" if plan.n_tc else "f32", "data": "synthetic",
+                "dtype": "f16 operands (RN from fp32 activations), f32 accumulate" if plan.n_tc else "f32", "data": "synthetic",
                 "config": {"workload": "configs[2]: DaNet forward batch=64 synthetic 224x224, HRNet-W%d + IUV_Renderer" % W,
                            "per_gpu_batch": B, "global_batch": B * world, "parallelism": "image-sharded x%d, one all_gather of para" % world,
-                           "conv_path": "tcgen05 TF32 (%d of %d convs) + fp32 FMA" % (plan.n_tc, prof["n_conv"]),
+                           "conv_path": "tcgen05 kind::f16 (%d of %d convs) + fp32 FMA" % (plan.n_tc, prof["n_conv"]),
                            "cuda_graph": not args.no_graph,
                            "l2": "inputs rotate over %d batches (%.0f MB > 126 MB L2); activations (%.1f GB/step) exceed L2"
                                  % (nrot, nrot * B * 3 * 224 * 224 * 4 / 1e6, plan.bytes_alloc / 1e9),
@@ -350,7 +359,7 @@ def profile_step(net, plan, x, dev):
     except Exception:
         pass
     n_conv = sum(1 for t, _, _ in events if t.startswith("conv"))
-    kern = "k_conv_tc (tcgen05 TF32) + k_conv_simt" if agg.get("conv_tc") else "k_conv_simt (fp32 FMA implicit GEMM)"
+    kern = "k_conv_tc (tcgen05 f16 -> f32 TMEM) + k_conv_simt" if agg.get("conv_tc") else "k_conv_simt (fp32 FMA implicit GEMM)"
     return {"conv_ms": conv_ms, "n_conv": n_conv, "conv_kernel": kern,
             "other_ms": {k: v for k, v in agg.items() if not k.startswith("conv")},
             "conv_tc_ms": agg.get("conv_tc", 0.0), "conv_simt_ms": agg.get("conv_simt", 0.0)}

@@ -22,7 +22,7 @@ def test_infer_net_fp32_matches_reference_golden(width):
 
 @pytest.mark.parametrize("width", [32, 48])
 def test_infer_net_tensor_core_path(width):
-    """TF32 tensor-core convolutions (where supported): tolerance scaled to TF32's 2^-11 rounding
+    """fp16-operand tensor-core convolutions (where supported): tolerance scaled to the 2^-11 operand rounding
     through ~100 layers; integer maps must agree where the reference margin exceeds 0.05."""
     net = build(width, DEV, conv_algo="tc")
     out = net.infer_net(make_image(2, 100).to(DEV))

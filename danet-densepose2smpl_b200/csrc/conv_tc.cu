@@ -41,7 +41,7 @@ constexpr int kWarpEpi = 8, kWarpB = 16, kWarpMma = 17;
 constexpr int kNumEpi = 256;             // two epilogue warps per TMEM lane quarter, each takes every other 16-column group
 constexpr int kNumProducers = 256;
 constexpr int kMaxBStages = 16;
-constexpr int kSmemBudget = 200 * 1024;  // one CTA per SM
+constexpr int kSmemBudget = 214 * 1024;  // one CTA per SM (227 KB max - static)
 constexpr int kSmemHalf = 100 * 1024;    // two CTAs per SM when everything fits
 constexpr bool kAllowTwoCtas = false;    // needs <= 73 registers/thread (currently 113): off
 
@@ -64,6 +64,7 @@ struct Geom {
     int a_stage_bytes, b_stage_bytes, tap_bytes, nb_stages, na_stages;
     int smem_bytes;
     int tmem_cols, ctas_per_sm, b_resident, variant;
+    int slabW, nslab, s_pitch, s_out_bytes;   // epilogue transposition buffer: 128 rows x (slabW + 4) floats
     int KS, acc_stages;                  // independent accumulators per tile (K split), TMEM accumulator stages
     long long blocks_per_set;            // packed weight blocks per weight set
 };
@@ -115,7 +116,11 @@ static bool make_geom(const danet_conv_desc* d, Geom* g) {
     while (cols < g->acc_stages * g->KS * g->NT) cols *= 2;
     g->tmem_cols = cols;
     const int taps = d->ksize * d->ksize;
-    const int fixed = 512 + 1024;
+    g->slabW = g->NT < 64 ? g->NT : 64;
+    g->nslab = (g->NT + g->slabW - 1) / g->slabW;
+    g->s_pitch = g->slabW + 4;
+    g->s_out_bytes = 128 * g->s_pitch * 4;
+    const int fixed = 512 + 1024 + g->s_out_bytes;
     // widest swizzle whose double-buffered halo + a minimal weight pipeline fits
     bool ok = false;
     for (int swb = 128; swb >= 32 && !ok; swb /= 2) {
@@ -294,6 +299,7 @@ k_conv_tc(const Args a) {
     const uint32_t bar_a_full = sBar, bar_a_empty = sBar + 24, bar_acc_full = sBar + 48, bar_acc_empty = sBar + 64;
     const uint32_t bar_b_full = sBar + 80, bar_b_empty = sBar + 80 + 8 * kMaxBStages;
     const uint32_t tmem_slot_addr = sBar + 80 + 16 * kMaxBStages;       // 80 + 256 + 4 <= 512
+    const uint32_t sOut = sBar + 512;                                   // epilogue transposition buffer (16-byte aligned)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -490,11 +496,17 @@ k_conv_tc(const Args a) {
         if (prof_on) { a.prof[4] = clock64() - t_start; a.prof[5] = prof_acc[0]; }
     } else if (warp < kWarpB) {
         // ================= epilogue: TMEM -> bias/residual/ReLU -> global =================
+        // Two phases per <=64-column slab so that every global access is a full-line coalesced 16-byte
+        // vector (the direct lane=row stores cost one L1 transaction per 16 bytes: ~4600 per tile):
+        //   A: lane = accumulator row: tcgen05.ld 16 columns, + bias, float4 stores into a padded
+        //      [128][slabW+4] smem tile;
+        //   B: lane = 16-byte channel chunk: consecutive lanes walk consecutive chunks of a pixel, then
+        //      the next pixel of the tile row (contiguous NHWC memory): + residual (prefetched into
+        //      registers BEFORE the accumulator wait), ReLU, coalesced store.
         const int q = warp & 3;                                  // TMEM lane quarter this warp may access
-        const int half = (warp - kWarpEpi) >> 2;                 // 0/1: which 16-column groups of the tile this warp owns
+        const int half = (warp - kWarpEpi) >> 2;                 // 0/1: which 16-column groups of a slab this warp owns
         const int m = q * 32 + lane;
-        const int hh = m >> 3, ww = m & 7;
-        const int ngroups = g.NT / 16;
+        const int et = threadIdx.x - kWarpEpi * 32;              // 0..255
         int cs = 0; uint32_t cph = 0;
         const bool prof_on = a.prof != nullptr && blockIdx.x == 0 && warp == kWarpEpi && lane == 0;
         long long prof_acc[1] = {0};
@@ -505,51 +517,76 @@ k_conv_tc(const Args a) {
             const int tw = r % g.tiles_w; r /= g.tiles_w;
             const int th = r % g.tiles_h;
             const int img = r / g.tiles_h;
-            const int oh = th * kTileH + hh, ow = tw * kTileW + ww;
-            const bool valid = oh < g.Ho && ow < g.Wo;
-            const size_t pix = ((size_t)img * g.Ho * g.Wo + (size_t)oh * g.Wo + ow) * g.Cout;
             const float* bias = a.bias ? a.bias + (size_t)(img % g.wsets) * g.Cout : nullptr;
-            // operands of the first group are fetched BEFORE waiting for the accumulator, and those of
-            // group i+1 while group i is processed: the global-load latency leaves the critical path
-            float4 rr[4], bb[4];
-            auto fetch = [&](int grp, float4* rv, float4* bv) {
+            const size_t img_base = (size_t)img * g.Ho * g.Wo;
+            bool waited = false;
+            for (int sl = 0; sl < g.nslab; ++sl) {
+                const int c_lo = sl * g.slabW;                             // first column of the slab inside the N tile
+                const int sw = min(g.slabW, g.NT - c_lo);                  // slab width (multiple of 16)
+                const int c4n = sw >> 2;                                   // float4 chunks per pixel in this slab
+                const int items = 128 * c4n;                               // <= 2048: at most 8 per thread
+                // ---- phase B operands first: residual prefetch (independent of the accumulator) ----
+                float4 rr[8];
+                size_t goff[8];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    rv[j] = make_float4(0.f, 0.f, 0.f, 0.f); bv[j] = rv[j];
-                    const int ch = nt * g.NT + grp * 16 + 4 * j;
-                    if (grp < ngroups && ch < g.Cout) {
-                        if (bias) bv[j] = __ldg(reinterpret_cast<const float4*>(bias + ch));
-                        if (a.res && valid) rv[j] = __ldg(reinterpret_cast<const float4*>(a.res + pix + ch));
-                    }
-                }
-            };
-            fetch(half, rr, bb);
-            { TC_PROF_BEGIN(); mbar_wait_sleep(bar_acc_full + 8 * cs, cph); TC_PROF_END(0); }
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cs * g.NT;
-            for (int grp = half; grp < ngroups; grp += 2) {
-                float v[16];
-                tc_ld16_nowait(taddr + grp * 16, v);
-                float4 rn[4], bn[4];
-                fetch(grp + 2, rn, bn);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (valid) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int ch = nt * g.NT + grp * 16 + 4 * j;
-                        if (ch < g.Cout) {
-                            float4 o = make_float4(v[4 * j] + bb[j].x + rr[j].x, v[4 * j + 1] + bb[j].y + rr[j].y,
-                                                   v[4 * j + 2] + bb[j].z + rr[j].z, v[4 * j + 3] + bb[j].w + rr[j].w);
-                            if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                            *reinterpret_cast<float4*>(a.y + pix + ch) = o;
+                for (int k = 0; k < 8; ++k) {
+                    rr[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    goff[k] = (size_t)-1;
+                    const int it = et + k * kNumEpi;
+                    if (it < items) {
+                        const int px = it / c4n, c4 = it - px * c4n;
+                        const int oh = th * kTileH + (px >> 3), ow = tw * kTileW + (px & 7);
+                        const int ch = nt * g.NT + c_lo + c4 * 4;
+                        if (oh < g.Ho && ow < g.Wo && ch < g.Cout) {
+                            goff[k] = (img_base + (size_t)oh * g.Wo + ow) * g.Cout + ch;
+                            if (a.res) rr[k] = __ldg(reinterpret_cast<const float4*>(a.res + goff[k]));
                         }
                     }
                 }
+                if (!waited) {
+                    TC_PROF_BEGIN(); mbar_wait_sleep(bar_acc_full + 8 * cs, cph); TC_PROF_END(0);
+                    tc_fence_after();
+                    waited = true;
+                }
+                // ---- phase A: TMEM -> (+bias) -> smem ----
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cs * g.NT + c_lo;
+                for (int grp = half; grp * 16 < sw; grp += 2) {
+                    float v[16];
+                    tc_ld16_nowait(taddr + grp * 16, v);
+                    float4 bb[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) { rr[j] = rn[j]; bb[j] = bn[j]; }
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int ch = nt * g.NT + c_lo + grp * 16 + 4 * jj;
+                        bb[jj] = (bias && ch < g.Cout) ? __ldg(reinterpret_cast<const float4*>(bias + ch)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    const uint32_t dsts = sOut + (uint32_t)(m * g.s_pitch + grp * 16) * 4;
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj)
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dsts + jj * 16), "f"(v[4 * jj] + bb[jj].x),
+                                     "f"(v[4 * jj + 1] + bb[jj].y), "f"(v[4 * jj + 2] + bb[jj].z), "f"(v[4 * jj + 3] + bb[jj].w) : "memory");
+                }
+                if (sl == g.nslab - 1) {                                   // accumulator fully drained: hand TMEM back early
+                    tc_fence_before();
+                    mbar_arrive(bar_acc_empty + 8 * cs);
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                // ---- phase B: smem -> (+residual, ReLU) -> coalesced global stores ----
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int it = et + k * kNumEpi;
+                    if (it < items && goff[k] != (size_t)-1) {
+                        const int px = it / c4n, c4 = it - px * c4n;
+                        float4 o;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
+                                     : "r"(sOut + (uint32_t)(px * g.s_pitch + c4 * 4) * 4) : "memory");
+                        o.x += rr[k].x; o.y += rr[k].y; o.z += rr[k].z; o.w += rr[k].w;
+                        if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                        *reinterpret_cast<float4*>(a.y + goff[k]) = o;
+                    }
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");              // smem tile free for the next slab / tile
             }
-            tc_fence_before();
-            mbar_arrive(bar_acc_empty + 8 * cs);
             if (++cs == g.acc_stages) { cs = 0; cph ^= 1; }
         }
         if (prof_on) { a.prof[6] = clock64() - t_start; a.prof[7] = prof_acc[0]; }
@@ -611,7 +648,7 @@ int conv_tc_launch(const danet_conv_desc* d, const float* x, const void* w_packe
         int dev = 0;
         DANET_CUDA(cudaGetDevice(&dev));
         DANET_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-        DANET_CUDA(cudaFuncSetAttribute(tc::k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        DANET_CUDA(cudaFuncSetAttribute(tc::k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
         attr_set = true;
     }
     const int cap = sm_count * a.g.ctas_per_sm;

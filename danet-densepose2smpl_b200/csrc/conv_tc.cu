@@ -38,6 +38,8 @@ constexpr int kThreads = 576;            // warps 0-7: A producers, warps 8-15: 
 // (the issue arbiter favours the highest warp id of a scheduler: the single MMA-issuing thread
 //  must not sit behind 12 warps that poll mbarriers -- measured 370 cycles/MMA when it did)
 constexpr int kWarpEpi = 8, kWarpB = 16, kWarpMma = 17;
+constexpr int kPollSleepNs = 0;           // mbarrier.try_wait already suspends the warp in hardware; an extra
+                                          // __nanosleep only added wake-up latency (about a microsecond per miss)
 constexpr int kNumEpi = 256;             // two epilogue warps per TMEM lane quarter, each takes every other 16-column group
 constexpr int kNumProducers = 256;
 constexpr int kMaxBStages = 16;
@@ -208,7 +210,7 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (done) return;
-        __nanosleep(40);
+        if (kPollSleepNs > 0) __nanosleep(kPollSleepNs);
     }
     __trap();
 }

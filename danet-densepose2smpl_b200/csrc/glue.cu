@@ -390,7 +390,8 @@ k_gcn_pose_head(int B, GcnArgs g, const float* __restrict__ rot_feats, const flo
 #pragma unroll
             for (int n = 0; n < 24; ++n) acc[n] = 0.f;
             const float* W = g.W[l];
-            for (int f = 0; f < F; ++f) {
+#pragma unroll 8
+            for (int f = 0; f < F; ++f) {                           // unrolled: 8 independent weight loads in flight
                 const float w = __ldg(W + (size_t)f * Fo + tid);
 #pragma unroll
                 for (int n = 0; n < 24; ++n) acc[n] = fmaf(s_ax[n * kGcnMaxF + f], w, acc[n]);

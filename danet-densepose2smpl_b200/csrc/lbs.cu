@@ -167,6 +167,9 @@ __global__ void k_smpl_pose(int B, int pose_kind, const float* __restrict__ beta
                             const float* __restrict__ pose, SmplView m, float* __restrict__ rot_out,
                             float* __restrict__ G, float* __restrict__ A, float* __restrict__ pf,
                             float* __restrict__ posed) {
+    // world transforms of the kinematic chain stay in shared memory (the parent's G is read back by
+    // the same thread; a global round trip cost ~1 us per joint)
+    __shared__ float s_G[32][kJ * 12 + 1];
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     float beta[kMaxBetas];
@@ -177,7 +180,7 @@ __global__ void k_smpl_pose(int B, int pose_kind, const float* __restrict__ beta
         for (int l = 0; l < m.nbetas; ++l) v = fmaf(beta[l], m.Jsd[e * m.nbetas + l], v);
         J[e] = v;
     }
-    float* Gb = G + (size_t)b * kJ * 12;
+    float* Gb = s_G[threadIdx.x];
     float* Ab = A + (size_t)b * kJ * 12;
     float* pfb = pf + (size_t)b * kPF;
     for (int i = 0; i < kJ; ++i) {
@@ -585,7 +588,7 @@ extern "C" int danet_smpl_forward(danet_smpl_t h, int32_t B, const float* betas,
     float* posed = (float*)(ws + ws_off(cur, (int64_t)B * kJ * 3 * 4));
     float* partials = (float*)(ws + ws_off(cur, (int64_t)B * (m.npairs > 0 ? m.npairs : 1) * 3 * 4));
 
-    k_smpl_pose<<<cdiv(B, 64), 64, 0, stream>>>(B, pose_kind, betas, pose, m, rotmats, G, A, pf, posed);
+    k_smpl_pose<<<cdiv(B, 32), 32, 0, stream>>>(B, pose_kind, betas, pose, m, rotmats, G, A, pf, posed);
     DANET_LAUNCH_CHECK();
     int nb = bodies_per_cta;
     if (nb <= 0) nb = B >= 2048 ? 16 : (B >= 32 ? 8 : (B >= 4 ? 4 : (B >= 2 ? 2 : 1)));

@@ -6,6 +6,8 @@ def main(path, out=None):
     agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
     for row in csv.DictReader(lines):
         name = row["Kernel Name"].split("(")[0]
+        if row.get("Metric Name", "gpu__time_duration.sum") != "gpu__time_duration.sum":
+            continue
         try:
             v = float(row["Metric Value"].replace(",", ""))
         except ValueError:

@@ -122,7 +122,7 @@ static bool make_geom(const danet_conv_desc* d, Geom* g) {
     g->nslab = (g->NT + g->slabW - 1) / g->slabW;
     g->s_pitch = g->slabW + 4;
     g->s_out_bytes = 128 * g->s_pitch * 4;
-    const int fixed = 512 + 1024 + g->s_out_bytes;
+    const int fixed = 512 + 1024;
     // widest swizzle whose double-buffered halo + a minimal weight pipeline fits
     bool ok = false;
     for (int swb = 128; swb >= 32 && !ok; swb /= 2) {
@@ -498,17 +498,16 @@ k_conv_tc(const Args a) {
         if (prof_on) { a.prof[4] = clock64() - t_start; a.prof[5] = prof_acc[0]; }
     } else if (warp < kWarpB) {
         // ================= epilogue: TMEM -> bias/residual/ReLU -> global =================
-        // Two phases per <=64-column slab so that every global access is a full-line coalesced 16-byte
-        // vector (the direct lane=row stores cost one L1 transaction per 16 bytes: ~4600 per tile):
-        //   A: lane = accumulator row: tcgen05.ld 16 columns, + bias, float4 stores into a padded
-        //      [128][slabW+4] smem tile;
-        //   B: lane = 16-byte channel chunk: consecutive lanes walk consecutive chunks of a pixel, then
-        //      the next pixel of the tile row (contiguous NHWC memory): + residual (prefetched into
-        //      registers BEFORE the accumulator wait), ReLU, coalesced store.
+        // lane = accumulator row (pixel); each of the two warps of a TMEM lane quarter takes every
+        // other 16-column group.  The residual operands of up to THREE groups ahead are held in
+        // registers and the first three are requested BEFORE the accumulator wait: one group
+        // iteration used to cost a full global-load latency (~1.5 us, profiles/r01_tc_role_cycles_v11.log).
+        // (A smem-staged, fully coalesced variant was measured slower: profiles/r01_tc_role_cycles_v12_*.)
         const int q = warp & 3;                                  // TMEM lane quarter this warp may access
-        const int half = (warp - kWarpEpi) >> 2;                 // 0/1: which 16-column groups of a slab this warp owns
+        const int half = (warp - kWarpEpi) >> 2;                 // 0/1: which 16-column groups of the tile this warp owns
         const int m = q * 32 + lane;
-        const int et = threadIdx.x - kWarpEpi * 32;              // 0..255
+        const int hh = m >> 3, ww = m & 7;
+        const int ngroups = g.NT / 16;
         int cs = 0; uint32_t cph = 0;
         const bool prof_on = a.prof != nullptr && blockIdx.x == 0 && warp == kWarpEpi && lane == 0;
         long long prof_acc[1] = {0};
@@ -519,76 +518,57 @@ k_conv_tc(const Args a) {
             const int tw = r % g.tiles_w; r /= g.tiles_w;
             const int th = r % g.tiles_h;
             const int img = r / g.tiles_h;
+            const int oh = th * kTileH + hh, ow = tw * kTileW + ww;
+            const bool valid = oh < g.Ho && ow < g.Wo;
+            const size_t pix = ((size_t)img * g.Ho * g.Wo + (size_t)oh * g.Wo + ow) * g.Cout;
             const float* bias = a.bias ? a.bias + (size_t)(img % g.wsets) * g.Cout : nullptr;
-            const size_t img_base = (size_t)img * g.Ho * g.Wo;
-            bool waited = false;
-            for (int sl = 0; sl < g.nslab; ++sl) {
-                const int c_lo = sl * g.slabW;                             // first column of the slab inside the N tile
-                const int sw = min(g.slabW, g.NT - c_lo);                  // slab width (multiple of 16)
-                const int c4n = sw >> 2;                                   // float4 chunks per pixel in this slab
-                const int items = 128 * c4n;                               // <= 2048: at most 8 per thread
-                // ---- phase B operands first: residual prefetch (independent of the accumulator) ----
-                float4 rr[8];
-                size_t goff[8];
+            const bool has_res = a.res != nullptr && valid;
+            auto fetch = [&](int grp, float4* rv) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    rr[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    goff[k] = (size_t)-1;
-                    const int it = et + k * kNumEpi;
-                    if (it < items) {
-                        const int px = it / c4n, c4 = it - px * c4n;
-                        const int oh = th * kTileH + (px >> 3), ow = tw * kTileW + (px & 7);
-                        const int ch = nt * g.NT + c_lo + c4 * 4;
-                        if (oh < g.Ho && ow < g.Wo && ch < g.Cout) {
-                            goff[k] = (img_base + (size_t)oh * g.Wo + ow) * g.Cout + ch;
-                            if (a.res) rr[k] = __ldg(reinterpret_cast<const float4*>(a.res + goff[k]));
-                        }
-                    }
+                for (int j = 0; j < 4; ++j) {
+                    rv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int ch = nt * g.NT + grp * 16 + 4 * j;
+                    if (has_res && grp < ngroups && ch < g.Cout) rv[j] = __ldg(reinterpret_cast<const float4*>(a.res + pix + ch));
                 }
-                if (!waited) {
-                    TC_PROF_BEGIN(); mbar_wait_sleep(bar_acc_full + 8 * cs, cph); TC_PROF_END(0);
-                    tc_fence_after();
-                    waited = true;
-                }
-                // ---- phase A: TMEM -> (+bias) -> smem ----
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cs * g.NT + c_lo;
-                for (int grp = half; grp * 16 < sw; grp += 2) {
-                    float v[16];
-                    tc_ld16_nowait(taddr + grp * 16, v);
-                    float4 bb[4];
+            };
+            auto finish = [&](int grp, const float* v, const float4* rv) {
+                if (!valid) return;
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const int ch = nt * g.NT + c_lo + grp * 16 + 4 * jj;
-                        bb[jj] = (bias && ch < g.Cout) ? __ldg(reinterpret_cast<const float4*>(bias + ch)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    const uint32_t dsts = sOut + (uint32_t)(m * g.s_pitch + grp * 16) * 4;
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj)
-                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dsts + jj * 16), "f"(v[4 * jj] + bb[jj].x),
-                                     "f"(v[4 * jj + 1] + bb[jj].y), "f"(v[4 * jj + 2] + bb[jj].z), "f"(v[4 * jj + 3] + bb[jj].w) : "memory");
-                }
-                if (sl == g.nslab - 1) {                                   // accumulator fully drained: hand TMEM back early
-                    tc_fence_before();
-                    mbar_arrive(bar_acc_empty + 8 * cs);
-                }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                // ---- phase B: smem -> (+residual, ReLU) -> coalesced global stores ----
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int it = et + k * kNumEpi;
-                    if (it < items && goff[k] != (size_t)-1) {
-                        const int px = it / c4n, c4 = it - px * c4n;
-                        float4 o;
-                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
-                                     : "r"(sOut + (uint32_t)(px * g.s_pitch + c4 * 4) * 4) : "memory");
-                        o.x += rr[k].x; o.y += rr[k].y; o.z += rr[k].z; o.w += rr[k].w;
+                for (int j = 0; j < 4; ++j) {
+                    const int ch = nt * g.NT + grp * 16 + 4 * j;
+                    if (ch < g.Cout) {
+                        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (bias) bb = __ldg(reinterpret_cast<const float4*>(bias + ch));
+                        float4 o = make_float4(v[4 * j] + bb.x + rv[j].x, v[4 * j + 1] + bb.y + rv[j].y,
+                                               v[4 * j + 2] + bb.z + rv[j].z, v[4 * j + 3] + bb.w + rv[j].w);
                         if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                        *reinterpret_cast<float4*>(a.y + goff[k]) = o;
+                        *reinterpret_cast<float4*>(a.y + pix + ch) = o;
                     }
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");              // smem tile free for the next slab / tile
+            };
+            float4 r0[4], r1[4], r2[4];
+            fetch(half, r0); fetch(half + 2, r1); fetch(half + 4, r2);
+            { TC_PROF_BEGIN(); mbar_wait_sleep(bar_acc_full + 8 * cs, cph); TC_PROF_END(0); }
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cs * g.NT;
+            for (int grp = half; grp < ngroups; grp += 6) {
+                float v[16];
+                tc_ld16(taddr + grp * 16, v);
+                finish(grp, v, r0);
+                fetch(grp + 6, r0);
+                if (grp + 2 < ngroups) {
+                    tc_ld16(taddr + (grp + 2) * 16, v);
+                    finish(grp + 2, v, r1);
+                    fetch(grp + 8, r1);
+                }
+                if (grp + 4 < ngroups) {
+                    tc_ld16(taddr + (grp + 4) * 16, v);
+                    finish(grp + 4, v, r2);
+                    fetch(grp + 10, r2);
+                }
             }
+            tc_fence_before();
+            mbar_arrive(bar_acc_empty + 8 * cs);
             if (++cs == g.acc_stages) { cs = 0; cph ^= 1; }
         }
         if (prof_on) { a.prof[6] = clock64() - t_start; a.prof[7] = prof_acc[0]; }

@@ -178,6 +178,10 @@ def run_b200_arm(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # libraries (NCCL's version banner) write to fd 1; keep stdout clean for the single JSON line
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if args.gpus > 1 and world == 1:
         raise SystemExit("bench.py --gpus %d must be launched with torchrun (one rank per GPU)" % args.gpus)
     torch.cuda.set_device(local)
@@ -300,7 +304,10 @@ def run_b200_arm(args):
                         "d2h_bytes_per_step": B * 229 * 4 + B * 3 * 56 * 56 * 4},
                 "gpu_launches": launches_per_step * args.steps,
                 "roofline": roof, "lbs": lbs, "cpu_baseline": cpu}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line))
+        sys.stdout.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

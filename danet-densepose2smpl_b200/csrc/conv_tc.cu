@@ -40,9 +40,7 @@ constexpr int kThreads = 576;            // warps 0-7: A producers, warps 8-15: 
 constexpr int kWarpEpi = 8, kWarpB = 16, kWarpMma = 17;
 constexpr int kPollSleepNs = 0;           // mbarrier.try_wait already suspends the warp in hardware; an extra
                                           // __nanosleep only added wake-up latency (about a microsecond per miss)
-constexpr int kNumEpi = 256;
-constexpr int kEpiPitch = 36;            // floats per row of a warp-private 32 x 32 transposition slab (+4 pad)
-constexpr int kEpiSmemBytes = 8 * 32 * kEpiPitch * 4;             // two epilogue warps per TMEM lane quarter, each takes every other 16-column group
+constexpr int kNumEpi = 256;             // two epilogue warps per TMEM lane quarter, each takes every other 16-column group
 constexpr int kNumProducers = 256;
 constexpr int kMaxBStages = 16;
 constexpr int kSmemBudget = 214 * 1024;  // one CTA per SM (227 KB max - static)
@@ -124,7 +122,7 @@ static bool make_geom(const danet_conv_desc* d, Geom* g) {
     g->nslab = (g->NT + g->slabW - 1) / g->slabW;
     g->s_pitch = g->slabW + 4;
     g->s_out_bytes = 128 * g->s_pitch * 4;
-    const int fixed = 512 + 1024 + kEpiSmemBytes;
+    const int fixed = 512 + 1024;
     // widest swizzle whose double-buffered halo + a minimal weight pipeline fits
     bool ok = false;
     for (int swb = 128; swb >= 32 && !ok; swb /= 2) {
@@ -307,7 +305,7 @@ k_conv_tc(const Args a) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full + 8 * i, 1); mbar_init(bar_acc_empty + 8 * i, kNumEpi / 2); }   // one 4-warp epilogue group drains a tile
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full + 8 * i, 1); mbar_init(bar_acc_empty + 8 * i, kNumEpi); }   // stage 1 unused when acc_stages == 1
         for (int i = 0; i < g.na_stages; ++i) { mbar_init(bar_a_full + 8 * i, kNumProducers); mbar_init(bar_a_empty + 8 * i, 1); }
         for (int i = 0; i < g.nb_stages; ++i) { mbar_init(bar_b_full + 8 * i, 1); mbar_init(bar_b_empty + 8 * i, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -500,91 +498,79 @@ k_conv_tc(const Args a) {
         if (prof_on) { a.prof[4] = clock64() - t_start; a.prof[5] = prof_acc[0]; }
     } else if (warp < kWarpB) {
         // ================= epilogue: TMEM -> bias/residual/ReLU -> global =================
-        // Two 4-warp groups alternate tiles (one warp per TMEM lane quarter = 4 tile rows x 8 pixels).
-        // Per 32-column slab each warp transposes its 32 x 32 block through a PRIVATE smem slab (no
-        // block barrier): phase A lane = accumulator row (tcgen05.ld, + bias, st.shared), phase B
-        // lane = 16-byte channel chunk of a pixel (+ residual, ReLU, 128-byte-contiguous stores).
-        // The lane = row direct stores cost one L1 wavefront per 16 bytes (~3000 per tile, the SM's
-        // load/store pipe was the limiter: profiles/r01_tc_role_cycles_v13.log); this needs ~4x fewer.
-        const int q = warp & 3;                                  // TMEM lane quarter of this warp
-        const int grp_id = (warp - kWarpEpi) >> 2;               // 0/1: tiles with (iteration % 2 == grp_id)
-        const uint32_t sSlab = sOut + (uint32_t)(warp - kWarpEpi) * (32 * kEpiPitch * 4);
-        const int nslab32 = (g.NT + 31) / 32;
+        // lane = accumulator row (pixel); each of the two warps of a TMEM lane quarter takes every
+        // other 16-column group.  The residual operands of up to THREE groups ahead are held in
+        // registers and the first three are requested BEFORE the accumulator wait: one group
+        // iteration used to cost a full global-load latency (~1.5 us, profiles/r01_tc_role_cycles_v11.log).
+        // (Two smem-staged, fully coalesced variants -- block-wide slabs and warp-private slabs with two
+        //  alternating warp groups -- were both measured SLOWER: profiles/r01_tc_role_cycles_v12_*, _v14_*.)
+        const int q = warp & 3;                                  // TMEM lane quarter this warp may access
+        const int half = (warp - kWarpEpi) >> 2;                 // 0/1: which 16-column groups of the tile this warp owns
+        const int m = q * 32 + lane;
+        const int hh = m >> 3, ww = m & 7;
+        const int ngroups = g.NT / 16;
+        int cs = 0; uint32_t cph = 0;
         const bool prof_on = a.prof != nullptr && blockIdx.x == 0 && warp == kWarpEpi && lane == 0;
         long long prof_acc[1] = {0};
         const long long t_start = prof_on ? clock64() : 0;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
-            if ((it & 1) != grp_id) continue;
-            const int cs = it % g.acc_stages;
-            const uint32_t cph = (uint32_t)(it / g.acc_stages) & 1u;
+        for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
             const int nt = tile % g.ntn;
             int r = tile / g.ntn;
             const int tw = r % g.tiles_w; r /= g.tiles_w;
             const int th = r % g.tiles_h;
             const int img = r / g.tiles_h;
+            const int oh = th * kTileH + hh, ow = tw * kTileW + ww;
+            const bool valid = oh < g.Ho && ow < g.Wo;
+            const size_t pix = ((size_t)img * g.Ho * g.Wo + (size_t)oh * g.Wo + ow) * g.Cout;
             const float* bias = a.bias ? a.bias + (size_t)(img % g.wsets) * g.Cout : nullptr;
-            const size_t img_base = (size_t)img * g.Ho * g.Wo;
-            const int oh0 = th * kTileH + q * 4, ow0 = tw * kTileW;
-            // residual operands of a slab in the coalesced (phase B) mapping
-            auto fetch = [&](int sl, float4* rv) {
-                const int sw = min(32, g.NT - sl * 32), c4sh = sw == 32 ? 3 : 2;
+            const bool has_res = a.res != nullptr && valid;
+            auto fetch = [&](int grp, float4* rv) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    rv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const int item = lane + 32 * k;
-                    const int px = item >> c4sh, c4 = item & ((1 << c4sh) - 1);
-                    const int oh = oh0 + (px >> 3), ow = ow0 + (px & 7), ch = nt * g.NT + sl * 32 + c4 * 4;
-                    if (a.res && sl < nslab32 && px < 32 && oh < g.Ho && ow < g.Wo && ch < g.Cout)
-                        rv[k] = __ldg(reinterpret_cast<const float4*>(a.res + (img_base + (size_t)oh * g.Wo + ow) * g.Cout + ch));
+                for (int j = 0; j < 4; ++j) {
+                    rv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int ch = nt * g.NT + grp * 16 + 4 * j;
+                    if (has_res && grp < ngroups && ch < g.Cout) rv[j] = __ldg(reinterpret_cast<const float4*>(a.res + pix + ch));
                 }
             };
-            float4 rr[8], rn[8];
-            fetch(0, rr);
+            auto finish = [&](int grp, const float* v, const float4* rv) {
+                if (!valid) return;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int ch = nt * g.NT + grp * 16 + 4 * j;
+                    if (ch < g.Cout) {
+                        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (bias) bb = __ldg(reinterpret_cast<const float4*>(bias + ch));
+                        float4 o = make_float4(v[4 * j] + bb.x + rv[j].x, v[4 * j + 1] + bb.y + rv[j].y,
+                                               v[4 * j + 2] + bb.z + rv[j].z, v[4 * j + 3] + bb.w + rv[j].w);
+                        if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                        *reinterpret_cast<float4*>(a.y + pix + ch) = o;
+                    }
+                }
+            };
+            float4 r0[4], r1[4], r2[4];
+            fetch(half, r0); fetch(half + 2, r1); fetch(half + 4, r2);
             { TC_PROF_BEGIN(); mbar_wait_sleep(bar_acc_full + 8 * cs, cph); TC_PROF_END(0); }
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cs * g.NT;
-            for (int sl = 0; sl < nslab32; ++sl) {
-                const int sw = min(32, g.NT - sl * 32), c4sh = sw == 32 ? 3 : 2;
-                fetch(sl + 1, rn);
-                // ---- phase A: lane = row ----
-                for (int h16 = 0; h16 * 16 < sw; ++h16) {
-                    float v[16];
-                    tc_ld16(taddr + sl * 32 + h16 * 16, v);
-                    const uint32_t dsts = sSlab + (uint32_t)(lane * kEpiPitch + h16 * 16) * 4;
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const int ch = nt * g.NT + sl * 32 + h16 * 16 + 4 * jj;
-                        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (bias && ch < g.Cout) bb = __ldg(reinterpret_cast<const float4*>(bias + ch));
-                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dsts + jj * 16), "f"(v[4 * jj] + bb.x),
-                                     "f"(v[4 * jj + 1] + bb.y), "f"(v[4 * jj + 2] + bb.z), "f"(v[4 * jj + 3] + bb.w) : "memory");
-                    }
+            for (int grp = half; grp < ngroups; grp += 6) {
+                float v[16];
+                tc_ld16(taddr + grp * 16, v);
+                finish(grp, v, r0);
+                fetch(grp + 6, r0);
+                if (grp + 2 < ngroups) {
+                    tc_ld16(taddr + (grp + 2) * 16, v);
+                    finish(grp + 2, v, r1);
+                    fetch(grp + 8, r1);
                 }
-                if (sl == nslab32 - 1) {                                   // accumulator drained: hand the TMEM stage back
-                    tc_fence_before();
-                    mbar_arrive(bar_acc_empty + 8 * cs);
+                if (grp + 4 < ngroups) {
+                    tc_ld16(taddr + (grp + 4) * 16, v);
+                    finish(grp + 4, v, r2);
+                    fetch(grp + 10, r2);
                 }
-                __syncwarp();
-                // ---- phase B: lane = 16-byte chunk, 128-byte-contiguous global accesses ----
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int item = lane + 32 * k;
-                    const int px = item >> c4sh, c4 = item & ((1 << c4sh) - 1);
-                    const int oh = oh0 + (px >> 3), ow = ow0 + (px & 7), ch = nt * g.NT + sl * 32 + c4 * 4;
-                    if (px < 32 && oh < g.Ho && ow < g.Wo && ch < g.Cout) {
-                        float4 o;
-                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
-                                     : "r"(sSlab + (uint32_t)(px * kEpiPitch + c4 * 4) * 4) : "memory");
-                        o.x += rr[k].x; o.y += rr[k].y; o.z += rr[k].z; o.w += rr[k].w;
-                        if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                        *reinterpret_cast<float4*>(a.y + (img_base + (size_t)oh * g.Wo + ow) * g.Cout + ch) = o;
-                    }
-                }
-                __syncwarp();
-#pragma unroll
-                for (int k = 0; k < 8; ++k) rr[k] = rn[k];
             }
+            tc_fence_before();
+            mbar_arrive(bar_acc_empty + 8 * cs);
+            if (++cs == g.acc_stages) { cs = 0; cph ^= 1; }
         }
         if (prof_on) { a.prof[6] = clock64() - t_start; a.prof[7] = prof_acc[0]; }
     }

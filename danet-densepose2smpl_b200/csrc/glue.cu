@@ -390,11 +390,16 @@ k_gcn_pose_head(int B, GcnArgs g, const float* __restrict__ rot_feats, const flo
 #pragma unroll
             for (int n = 0; n < 24; ++n) acc[n] = 0.f;
             const float* W = g.W[l];
-#pragma unroll 8
-            for (int f = 0; f < F; ++f) {                           // unrolled: 8 independent weight loads in flight
-                const float w = __ldg(W + (size_t)f * Fo + tid);
+            // 4 input features per step: 4 independent weight loads in flight and one 16-byte
+            // broadcast smem read per node instead of four scalar ones (the loop was LDS-bound)
+            for (int f = 0; f < F; f += 4) {
+                const float w0 = __ldg(W + (size_t)f * Fo + tid), w1 = __ldg(W + (size_t)(f + 1) * Fo + tid);
+                const float w2 = __ldg(W + (size_t)(f + 2) * Fo + tid), w3 = __ldg(W + (size_t)(f + 3) * Fo + tid);
 #pragma unroll
-                for (int n = 0; n < 24; ++n) acc[n] = fmaf(s_ax[n * kGcnMaxF + f], w, acc[n]);
+                for (int n = 0; n < 24; ++n) {
+                    const float4 av = *reinterpret_cast<const float4*>(&s_ax[n * kGcnMaxF + f]);
+                    acc[n] = fmaf(av.x, w0, fmaf(av.y, w1, fmaf(av.z, w2, fmaf(av.w, w3, acc[n]))));
+                }
             }
             const float bias = g.b[l][tid];
 #pragma unroll
@@ -550,8 +555,9 @@ extern "C" int danet_gcn_pose_head(int32_t B, const danet_gcn_params* p, const f
     g.adj = p->adj; g.head_w = p->head_w; g.head_b = p->head_b; g.mean_pose = p->mean_pose;
     for (int l = 0; l < 5; ++l) {
         DANET_CHECK(p->W[l] && p->b[l] && p->bn_scale[l] && p->bn_shift[l], "danet_gcn_pose_head: layer %d has null params", l);
-        DANET_CHECK(p->dim_in[l] > 0 && p->dim_in[l] <= kGcnMaxF && p->dim_out[l] > 0 && p->dim_out[l] <= kGcnMaxF,
-                    "danet_gcn_pose_head: layer %d dims %d->%d exceed %d", l, p->dim_in[l], p->dim_out[l], kGcnMaxF);
+        DANET_CHECK(p->dim_in[l] > 0 && p->dim_in[l] <= kGcnMaxF && p->dim_out[l] > 0 && p->dim_out[l] <= kGcnMaxF &&
+                    p->dim_in[l] % 4 == 0,
+                    "danet_gcn_pose_head: layer %d dims %d->%d must be <= %d and the input a multiple of 4", l, p->dim_in[l], p->dim_out[l], kGcnMaxF);
         g.W[l] = p->W[l]; g.b[l] = p->b[l]; g.bn_s[l] = p->bn_scale[l]; g.bn_t[l] = p->bn_shift[l];
         g.din[l] = p->dim_in[l]; g.dout[l] = p->dim_out[l];
     }

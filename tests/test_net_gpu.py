@@ -59,3 +59,20 @@ def test_demo_chain_matches_oracle():
     mesh = synth.make_dp_mesh(0)
     rimg, _, _ = raster.verts2uvimg(out.vertices.cpu().numpy(), cam.cpu().numpy(), mesh, synth.dp_textures(mesh))
     np.testing.assert_array_equal(img.cpu().numpy(), rimg)
+
+
+def test_evaluate_batch_matches_oracle_mpjpe():
+    """eval.py:166-212 chain on the GPU vs the numpy oracle (same para -> same joints -> same MPJPE)."""
+    from danet_b200.evaluate import evaluate_batch
+    from oracle import lbs, synth
+    net = build(32, DEV, conv_algo="simt")
+    img = make_image(3, 100).to(DEV)
+    g = torch.Generator().manual_seed(3)
+    gt = (torch.randn(3, 14, 3, generator=g) * 0.2).to(DEV)
+    out = evaluate_batch(net, net.iuv2smpl.smpl, img, gt)
+    para = out["para"].cpu().numpy()
+    R = para[:, 13:].reshape(-1, 24, 3, 3)
+    ref = lbs.smpl_forward(synth.make_smpl_model(0), para[:, 3:13], R[:, 1:], R[:, :1], pose2rot=False, dtype=np.float64)
+    want = lbs.mpjpe_h36m(ref["joints_h36m"], gt.cpu().numpy().astype(np.float64))
+    np.testing.assert_allclose(out["mpjpe"].cpu().numpy(), want, atol=1e-5)
+    assert out["pred_j14"].shape == (3, 14, 3)

@@ -277,6 +277,19 @@ __device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, float* v) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// 16 lanes x 256 bits, twice (columns +0..7 and +8..15): thread t receives, for i = 0/1,
+// r[4i], r[4i+1] = row t/4, columns 8i + 2*(t%4) + {0,1};  r[4i+2], r[4i+3] = row t/4 + 8, same columns
+// (the mma m16n8 accumulator fragment).  A quad then owns 32 contiguous bytes of a row.
+__device__ __forceinline__ void tc_ld16x256_x2_nowait(uint32_t taddr, float* v) {
+    uint32_t r[8];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
     uint32_t r;
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));   // d = {hi -> upper, lo -> lower}
@@ -563,14 +576,92 @@ k_conv_tc(const Args a) {
         //  alternating warp groups -- were both measured SLOWER: profiles/r01_tc_role_cycles_v12_*, _v14_*.)
         const int q = warp & 3;                                  // TMEM lane quarter this warp may access
         const int half = (warp - kWarpEpi) >> 2;                 // 0/1: which 16-column groups of the tile this warp owns
-        const int m = q * 32 + lane;
-        const int hh = m >> 3, ww = m & 7;
         const int ngroups = g.NT / 16;
         int cs = 0; uint32_t cph = 0;
         pdl_wait();                                              // residual reads / output writes
         const bool prof_on = PROF && a.prof != nullptr && blockIdx.x == 0 && warp == kWarpEpi && lane == 0;
         long long prof_acc[1] = {0};
         const long long t_start = prof_on ? clock64() : 0;
+        if (!(g.variant & 1)) {
+            // Quad mapping (tcgen05.ld 16x256b): a thread owns tile column ww = lane/4 of the four tile rows
+            // 4q..4q+3 and, per 16-column group, channels 2*(lane%4)+{0,1} and +8: the four lanes of a quad
+            // read/write one whole 32-byte sector, a warp instruction touches 8 lines instead of 32.  The
+            // lane = row mapping (16 bytes per line per instruction) made the load/store pipe the limiter of
+            // the epilogue: 8-9 us for one exposed 128 x 192 tile (per-CTA timeline in profiles/).
+            const int wwq = lane >> 2, cq = 2 * (lane & 3);
+            for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+                int nt, tw, th, img;
+                decode_tile(g, tile, nt, tw, th, img);
+                const int ow = tw * kTileW + wwq, oh0 = th * kTileH + 4 * q;
+                const size_t pix0 = ((size_t)img * g.Ho * g.Wo + (size_t)oh0 * g.Wo + ow) * g.Cout + nt * g.NT + cq;
+                const size_t rowstep = (size_t)g.Wo * g.Cout;
+                const int nrows = ow < g.Wo ? min(4, g.Ho - oh0) : 0;        // valid tile rows of this thread (<= 0: none)
+                const int chlim = g.Cout - nt * g.NT - cq;                   // channel offsets below this are real
+                const float* bias = a.bias ? a.bias + (size_t)(img - mdiv(img, g.m_ws) * g.wsets) * g.Cout + nt * g.NT + cq : nullptr;
+                const bool has_res = a.res != nullptr;
+                auto fetch = [&](int grp, float2* rv) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            rv[2 * k + i] = make_float2(0.f, 0.f);
+                            const int co = grp * 16 + 8 * i;
+                            if (has_res && grp < ngroups && k < nrows && co < chlim)
+                                rv[2 * k + i] = __ldg(reinterpret_cast<const float2*>(a.res + pix0 + k * rowstep + co));
+                        }
+                };
+                auto finish = [&](int grp, const float* va, const float* vb, const float2* rv) {
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int co = grp * 16 + 8 * i;
+                        if (co >= chlim) continue;
+                        float2 bb = make_float2(0.f, 0.f);
+                        if (bias) bb = __ldg(reinterpret_cast<const float2*>(bias + co));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (k >= nrows) continue;
+                            const float* v = (k < 2 ? va : vb) + 4 * i + 2 * (k & 1);
+                            float2 o = make_float2(v[0] + bb.x + rv[2 * k + i].x, v[1] + bb.y + rv[2 * k + i].y);
+                            if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); }
+                            *reinterpret_cast<float2*>(a.y + pix0 + k * rowstep + co) = o;
+                        }
+                    }
+                };
+                float2 r0[8], r1[8], r2[8];
+                fetch(half, r0); fetch(half + 2, r1); fetch(half + 4, r2);
+                { TC_PROF_BEGIN(); mbar_wait_sleep(bar_acc_full + 8 * cs, cph); TC_PROF_END(0); }
+                if (PROF && tl && warp == kWarpEpi && lane == 0 && tile == (int)blockIdx.x) tl[6] = clock64() - t_entry;
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cs * g.NT;
+                for (int grp = half; grp < ngroups; grp += 6) {
+                    float va[8], vb[8];
+                    tc_ld16x256_x2_nowait(taddr + grp * 16, va);
+                    tc_ld16x256_x2_nowait(taddr + (16u << 16) + grp * 16, vb);
+                    tc_wait_ld();
+                    finish(grp, va, vb, r0);
+                    fetch(grp + 6, r0);
+                    if (grp + 2 < ngroups) {
+                        tc_ld16x256_x2_nowait(taddr + (grp + 2) * 16, va);
+                        tc_ld16x256_x2_nowait(taddr + (16u << 16) + (grp + 2) * 16, vb);
+                        tc_wait_ld();
+                        finish(grp + 2, va, vb, r1);
+                        fetch(grp + 8, r1);
+                    }
+                    if (grp + 4 < ngroups) {
+                        tc_ld16x256_x2_nowait(taddr + (grp + 4) * 16, va);
+                        tc_ld16x256_x2_nowait(taddr + (16u << 16) + (grp + 4) * 16, vb);
+                        tc_wait_ld();
+                        finish(grp + 4, va, vb, r2);
+                        fetch(grp + 10, r2);
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(bar_acc_empty + 8 * cs);
+                if (++cs == g.acc_stages) { cs = 0; cph ^= 1; }
+            }
+        } else {
+        const int m = q * 32 + lane;
+        const int hh = m >> 3, ww = m & 7;
         for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
             int nt, tw, th, img;
             decode_tile(g, tile, nt, tw, th, img);
@@ -627,6 +718,7 @@ k_conv_tc(const Args a) {
             tc_fence_before();
             mbar_arrive(bar_acc_empty + 8 * cs);
             if (++cs == g.acc_stages) { cs = 0; cph ^= 1; }
+        }
         }
         if (prof_on) { a.prof[6] = clock64() - t_start; a.prof[7] = prof_acc[0]; }
         if (PROF && tl && warp == kWarpEpi && lane == 0) tl[7] = clock64() - t_entry;

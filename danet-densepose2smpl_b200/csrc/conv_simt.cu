@@ -5,53 +5,58 @@
 // as `wsets` weight sets over the (batch,part)-flattened image axis (see include/danet_b200.h).
 //
 // CTA tile: 64 (image, output pixel) rows of one weight set x 64 output channels, 256 threads, 4x4 outputs per
-// thread, K streamed in (tap, 16-channel) chunks through shared memory with register prefetch.
+// thread (32 x 32, 2x2 per thread, when the 64 x 64 grid would have fewer than 120 CTAs), K streamed in
+// (tap, 16-channel) chunks through shared memory with register prefetch.
 #include "common.cuh"
 
 namespace danet {
 
-constexpr int kTP = 64;      // pixels per CTA
-constexpr int kTCo = 64;     // output channels per CTA
 constexpr int kKC = 16;      // input channels per K chunk
-constexpr int kAPitch = kTP + 4;
 
 struct ConvArgs {
     int N, H, W, Cin, Cout, ks, stride, pad, Ho, Wo, wsets, relu;
     const float* x; const float* w; const float* bias; const float* res; float* y;
 };
 
+// TM x TN output tile per CTA (64x64: 4x4 outputs per thread; 32x32: 2x2, for problems whose 64x64
+// grid would leave most SMs idle, e.g. the 2x2-pixel 512-channel layers of the ResNet tail)
+template <int TM, int TN>
 __global__ void __launch_bounds__(256)
 k_conv_simt(ConvArgs a) {
-    __shared__ __align__(16) float As[kKC][kAPitch];
-    __shared__ __align__(16) float Bs[kKC][kTCo];
+    constexpr int MT = TM / 16, NTH = TN / 16;       // outputs per thread
+    constexpr int APITCH = TM + 4;
+    __shared__ __align__(16) float As[kKC][APITCH];
+    __shared__ __align__(16) float Bs[kKC][TN];
     // rows of the implicit GEMM = (image of this weight set, output pixel), flattened: image
-    // n = g + wsets * (row / HoWo).  Tiny maps (4x4, 2x2) then still fill the 64-row tile.
+    // n = g + wsets * (row / HoWo).  Tiny maps (4x4, 2x2) then still fill the row tile.
     const int tid = threadIdx.x;
     const int g = blockIdx.z;
-    const int q0 = blockIdx.x * kTP;
-    const int co0 = blockIdx.y * kTCo;
+    const int q0 = blockIdx.x * TM;
+    const int co0 = blockIdx.y * TN;
     const int HoWo = a.Ho * a.Wo;
     const int rows = ((a.N - g + a.wsets - 1) / a.wsets) * HoWo;
     const int K = a.ks * a.ks * a.Cin;
     const float* wg = a.w + (size_t)g * K * a.Cout;
 
-    // A-load role: row lp = tid/4, channel vec lv = tid%4
+    // A-load role (threads < TM*4): row lp = tid/4, channel vec lv = tid%4
+    const bool a_role = tid < TM * 4;
     const int lp = tid >> 2, lv = tid & 3;
     const int lq = q0 + lp;
-    const bool lvalid = lq < rows;
+    const bool lvalid = a_role && lq < rows;
     const int lk = lvalid ? lq / HoWo : 0, lpix = lvalid ? lq - lk * HoWo : 0;
     const int loh = lpix / a.Wo, low = lpix - loh * a.Wo;
     const float* xn = a.x + (size_t)(g + a.wsets * lk) * a.H * a.W * a.Cin;
-    // B-load role: row bk = tid/16, col vec bv = tid%16
-    const int bk = tid >> 4, bv = tid & 15;
+    // B-load role (threads < 16*TN/4): row bk, col vec bv
+    const bool b_role = tid < kKC * (TN / 4);
+    const int bk = tid / (TN / 4), bv = tid % (TN / 4);
     // compute role
     const int ty = tid >> 4, tx = tid & 15;
 
-    float acc[4][4];
+    float acc[MT][NTH];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < MT; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < NTH; ++j) acc[i][j] = 0.f;
 
     const int cchunks = (a.Cin + kKC - 1) / kKC;
     const int nchunks = a.ks * a.ks * cchunks;
@@ -66,48 +71,62 @@ k_conv_simt(ConvArgs a) {
             ra = __ldg(reinterpret_cast<const float4*>(xn + ((size_t)ih * a.W + iw) * a.Cin + c));
         rb = make_float4(0.f, 0.f, 0.f, 0.f);
         const int kc = c0 + bk, co = co0 + bv * 4;
-        if (kc < a.Cin && co < a.Cout)
+        if (b_role && kc < a.Cin && co < a.Cout)
             rb = __ldg(reinterpret_cast<const float4*>(wg + ((size_t)tap * a.Cin + kc) * a.Cout + co));
     };
 
     float4 ra, rb;
     load(0, ra, rb);
     for (int chunk = 0; chunk < nchunks; ++chunk) {
-        As[lv * 4 + 0][lp] = ra.x; As[lv * 4 + 1][lp] = ra.y; As[lv * 4 + 2][lp] = ra.z; As[lv * 4 + 3][lp] = ra.w;
-        *reinterpret_cast<float4*>(&Bs[bk][bv * 4]) = rb;
+        if (a_role) { As[lv * 4 + 0][lp] = ra.x; As[lv * 4 + 1][lp] = ra.y; As[lv * 4 + 2][lp] = ra.z; As[lv * 4 + 3][lp] = ra.w; }
+        if (b_role) *reinterpret_cast<float4*>(&Bs[bk][bv * 4]) = rb;
         __syncthreads();
         if (chunk + 1 < nchunks) load(chunk + 1, ra, rb);
 #pragma unroll
         for (int k = 0; k < kKC; ++k) {
-            const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-            const float4 bv4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-            const float am[4] = {av.x, av.y, av.z, av.w};
-            const float bm[4] = {bv4.x, bv4.y, bv4.z, bv4.w};
+            float am[MT], bm[NTH];
+            if (MT == 4) {
+                const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+                am[0] = av.x; am[1] = av.y; am[MT - 2] = av.z; am[MT - 1] = av.w;
+            } else {
+                const float2 av = *reinterpret_cast<const float2*>(&As[k][ty * 2]);
+                am[0] = av.x; am[1] = av.y;
+            }
+            if (NTH == 4) {
+                const float4 bv4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+                bm[0] = bv4.x; bm[1] = bv4.y; bm[NTH - 2] = bv4.z; bm[NTH - 1] = bv4.w;
+            } else {
+                const float2 bv2 = *reinterpret_cast<const float2*>(&Bs[k][tx * 2]);
+                bm[0] = bv2.x; bm[1] = bv2.y;
+            }
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < MT; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(am[i], bm[j], acc[i][j]);
+                for (int j = 0; j < NTH; ++j) acc[i][j] = fmaf(am[i], bm[j], acc[i][j]);
         }
         __syncthreads();
     }
 
-    const int co = co0 + tx * 4;
+    const int co = co0 + tx * NTH;
     if (co >= a.Cout) return;
-    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (a.bias) bias = __ldg(reinterpret_cast<const float4*>(a.bias + (size_t)g * a.Cout + co));
+    float bias[NTH];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int q = q0 + ty * 4 + i;
+    for (int j = 0; j < NTH; ++j) bias[j] = a.bias ? __ldg(a.bias + (size_t)g * a.Cout + co + j) : 0.f;
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+        const int q = q0 + ty * MT + i;
         if (q >= rows) continue;
         const int qk = q / HoWo, qp = q - qk * HoWo;
         const size_t o = ((size_t)(g + a.wsets * qk) * HoWo + qp) * a.Cout + co;
-        float4 v = make_float4(acc[i][0] + bias.x, acc[i][1] + bias.y, acc[i][2] + bias.z, acc[i][3] + bias.w);
-        if (a.res) {
-            const float4 rr = __ldg(reinterpret_cast<const float4*>(a.res + o));
-            v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+        float v[NTH];
+#pragma unroll
+        for (int j = 0; j < NTH; ++j) {
+            v[j] = acc[i][j] + bias[j];
+            if (a.res) v[j] += __ldg(a.res + o + j);
+            if (a.relu) v[j] = fmaxf(v[j], 0.f);
         }
-        if (a.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-        *reinterpret_cast<float4*>(a.y + o) = v;
+        if (NTH == 4) *reinterpret_cast<float4*>(a.y + o) = make_float4(v[0], v[1], v[NTH - 2], v[NTH - 1]);
+        else *reinterpret_cast<float2*>(a.y + o) = make_float2(v[0], v[1]);
     }
 }
 
@@ -120,8 +139,14 @@ int conv_simt_launch(const danet_conv_desc* d, const float* x, const float* w, c
     a.Wo = (d->W + 2 * d->pad - d->ksize) / d->stride + 1;
     a.x = x; a.w = w; a.bias = bias; a.res = residual; a.y = y;
     const int rows = cdiv(a.N, a.wsets) * a.Ho * a.Wo;
-    dim3 grid(cdiv(rows, kTP), cdiv(a.Cout, kTCo), a.wsets);
-    k_conv_simt<<<grid, 256, 0, stream>>>(a);
+    const long long ctas64 = (long long)cdiv(rows, 64) * cdiv(a.Cout, 64) * a.wsets;
+    if (ctas64 < 120) {
+        dim3 grid(cdiv(rows, 32), cdiv(a.Cout, 32), a.wsets);
+        k_conv_simt<32, 32><<<grid, 256, 0, stream>>>(a);
+    } else {
+        dim3 grid(cdiv(rows, 64), cdiv(a.Cout, 64), a.wsets);
+        k_conv_simt<64, 64><<<grid, 256, 0, stream>>>(a);
+    }
     DANET_LAUNCH_CHECK();
     return 0;
 }

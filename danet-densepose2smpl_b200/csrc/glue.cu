@@ -73,25 +73,46 @@ __global__ void k_iuv_clean_global(int B, int HW, int Chead, int off_u, int off_
     }
 }
 
-// 24 per-part iuvmap_clean calls of danet.py:93-98 in one pass
+// 24 per-part iuvmap_clean calls of danet.py:93-98 in one pass (one thread per pixel; rows are read and
+// written as 16-byte vectors when Cx, Cy are multiples of 4 -- they are, the graph pads channels)
+template <bool VEC>
 __global__ void k_iuv_clean_parts(int N, int HW, int Cx, int Cy, const float* __restrict__ x,
                                   float* __restrict__ y, float* raw) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)N * HW) return;
     const float* h = x + i * Cx;
-    float v[21];
+    float v[24];
+    if (VEC) {
 #pragma unroll
-    for (int c = 0; c < 21; ++c) v[c] = h[c];
+        for (int c = 0; c < 6; ++c) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(h) + c);
+            v[4 * c] = t.x; v[4 * c + 1] = t.y; v[4 * c + 2] = t.z; v[4 * c + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 21; ++c) v[c] = h[c];
+    }
     const int best = argmax_first(v + 14, 7);
     float* o = y + i * Cy;
+    float ov[24];
 #pragma unroll
     for (int c = 0; c < 7; ++c) {
         const float oh = (c == best) ? 1.0f : 0.0f;
-        o[c] = oh * v[c]; o[7 + c] = oh * v[7 + c]; o[14 + c] = oh;
+        ov[c] = oh * v[c]; ov[7 + c] = oh * v[7 + c]; ov[14 + c] = oh;
     }
-    for (int c = 21; c < Cy; ++c) o[c] = 0.0f;
+    ov[21] = ov[22] = ov[23] = 0.0f;
+    if (VEC) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c)
+            reinterpret_cast<float4*>(o)[c] = make_float4(ov[4 * c], ov[4 * c + 1], ov[4 * c + 2], ov[4 * c + 3]);
+        for (int c = 24; c < Cy; ++c) o[c] = 0.0f;
+    } else {
+#pragma unroll
+        for (int c = 0; c < 21; ++c) o[c] = ov[c];
+        for (int c = 21; c < Cy; ++c) o[c] = 0.0f;
+    }
     if (raw) {
-        const size_t n = i / HW, pix = i % HW;
+        const size_t n = i / HW, pix = i - n * HW;
 #pragma unroll
         for (int c = 0; c < 21; ++c) raw[(n * 21 + c) * HW + pix] = v[c];
     }
@@ -217,47 +238,60 @@ k_stn_params(int B, int S, int Chm, const float* __restrict__ hm, const uint8_t*
 }
 
 // 24x affine_grid + grid_sample (iuv_estimator.py:193-204), C % 4 == 0
-__global__ void k_stn_sample(int B, int S, int C, const float* __restrict__ xd, const float* __restrict__ theta,
-                             int align_corners, float* __restrict__ crops) {
+// grid = one block per (crop b*24+part, output row py); threads run over (px, 4-channel group) of the row: the
+// per-element 64-bit div/mod chain of the first version cost more than the 16-byte store it fed
+__global__ void __launch_bounds__(256)
+k_stn_sample(int B, int S, int C, const float* __restrict__ xd, const float* __restrict__ theta,
+             int align_corners, float* __restrict__ crops) {
     const int C4 = C >> 2;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t total = (size_t)B * 24 * S * S * C4;
-    if (i >= total) return;
-    const int c4 = (int)(i % C4);
-    size_t r = i / C4;
-    const int px = (int)(r % S); r /= S;
-    const int py = (int)(r % S); r /= S;
-    const int part = (int)(r % 24);
-    const int b = (int)(r / 24);
-    const float* t = theta + ((size_t)b * 24 + part) * 3;
+    const int bp = blockIdx.x / S, py = blockIdx.x - bp * S;
+    const int b = bp / 24;
+    const float* t = theta + (size_t)bp * 3;
     const float s = t[0], cx = t[1], cy = t[2];
-    float xb, yb;
-    if (align_corners) { xb = -1.0f + 2.0f * (float)px / (float)(S - 1); yb = -1.0f + 2.0f * (float)py / (float)(S - 1); }
-    else { xb = (float)(2 * px + 1) / (float)S - 1.0f; yb = (float)(2 * py + 1) / (float)S - 1.0f; }
-    const float gx = s * xb + cx, gy = s * yb + cy;
-    float ix, iy;
-    if (align_corners) { ix = (gx + 1.0f) * 0.5f * (float)(S - 1); iy = (gy + 1.0f) * 0.5f * (float)(S - 1); }
-    else { ix = ((gx + 1.0f) * (float)S - 1.0f) * 0.5f; iy = ((gy + 1.0f) * (float)S - 1.0f) * 0.5f; }
-    const float fx = floorf(ix), fy = floorf(iy);
-    const float tx = ix - fx, ty = iy - fy;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    // guard against huge coordinates before the int conversion
-    if (fx > -2.0f && fx < (float)S + 1.0f && fy > -2.0f && fy < (float)S + 1.0f) {
-        const int x0 = (int)fx, y0 = (int)fy;
-        const float* base = xd + (size_t)b * S * S * C + (size_t)c4 * 4;
+    float yb;
+    if (align_corners) yb = -1.0f + 2.0f * (float)py / (float)(S - 1);
+    else yb = (float)(2 * py + 1) / (float)S - 1.0f;
+    const float gy = s * yb + cy;
+    float iy;
+    if (align_corners) iy = (gy + 1.0f) * 0.5f * (float)(S - 1);
+    else iy = ((gy + 1.0f) * (float)S - 1.0f) * 0.5f;
+    const float fy = floorf(iy);
+    const float ty = iy - fy;
+    const bool y_ok = fy > -2.0f && fy < (float)S + 1.0f;
+    const int y0 = y_ok ? (int)fy : 0;
+    const float* img = xd + (size_t)b * S * S * C;
+    float4* out = reinterpret_cast<float4*>(crops) + ((size_t)bp * S + py) * S * C4;
+    const int items = S * C4;
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {
+        const int px = i / C4, c4 = i - px * C4;
+        float xb;
+        if (align_corners) xb = -1.0f + 2.0f * (float)px / (float)(S - 1);
+        else xb = (float)(2 * px + 1) / (float)S - 1.0f;
+        const float gx = s * xb + cx;
+        float ix;
+        if (align_corners) ix = (gx + 1.0f) * 0.5f * (float)(S - 1);
+        else ix = ((gx + 1.0f) * (float)S - 1.0f) * 0.5f;
+        const float fx = floorf(ix);
+        const float tx = ix - fx;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        // guard against huge coordinates before the int conversion
+        if (y_ok && fx > -2.0f && fx < (float)S + 1.0f) {
+            const int x0 = (int)fx;
+            const float* base = img + c4 * 4;
 #pragma unroll
-        for (int dy = 0; dy < 2; ++dy)
+            for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-            for (int dx = 0; dx < 2; ++dx) {
-                const int xx = x0 + dx, yy = y0 + dy;
-                if (xx < 0 || xx >= S || yy < 0 || yy >= S) continue;
-                const float w = (dx ? tx : 1.0f - tx) * (dy ? ty : 1.0f - ty);
-                const float4 v = __ldg(reinterpret_cast<const float4*>(base + ((size_t)yy * S + xx) * C));
-                acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
-                acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
-            }
+                for (int dx = 0; dx < 2; ++dx) {
+                    const int xx = x0 + dx, yy = y0 + dy;
+                    if (xx < 0 || xx >= S || yy < 0 || yy >= S) continue;
+                    const float w = (dx ? tx : 1.0f - tx) * (dy ? ty : 1.0f - ty);
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(base + (size_t)(yy * S + xx) * C));
+                    acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
+                    acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+                }
+        }
+        out[i] = acc;
     }
-    reinterpret_cast<float4*>(crops)[i] = acc;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -265,38 +299,35 @@ __global__ void k_stn_sample(int B, int S, int C, const float* __restrict__ xd, 
 // ------------------------------------------------------------------------------------------
 struct FuseArgs { const float* t[4]; int f[4]; int n; };
 
-__global__ void k_fuse_sum(int N, int H, int W, int C4, FuseArgs a, int relu, float* __restrict__ y) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t total = (size_t)N * H * W * C4;
-    if (i >= total) return;
-    const int c4 = (int)(i % C4);
-    size_t r = i / C4;
-    const int w = (int)(r % W); r /= W;
-    const int h = (int)(r % H);
-    const int n = (int)(r / H);
+// grid = (n*H + h, chunks of a row): no per-element 64-bit division
+__global__ void __launch_bounds__(256)
+k_fuse_sum(int N, int H, int W, int C4, FuseArgs a, int relu, float* __restrict__ y) {
+    const int row = blockIdx.x;
+    const int n = row / H, h = row - n * H;
+    const int i = blockIdx.y * blockDim.x + threadIdx.x;
+    if (i >= W * C4) return;
+    const int w = i / C4, c4 = i - w * C4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int j = 0; j < a.n; ++j) {
         const int f = a.f[j];
         const int hh = H / f, ww = W / f;
         const float4 v = __ldg(reinterpret_cast<const float4*>(a.t[j]) +
-                               (((size_t)n * hh + h / f) * ww + w / f) * C4 + c4);
+                               ((size_t)(n * hh + h / f) * ww + w / f) * C4 + c4);
         if (j == 0) acc = v;
         else { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
     }
     if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
-    reinterpret_cast<float4*>(y)[i] = acc;
+    reinterpret_cast<float4*>(y)[(size_t)row * W * C4 + i] = acc;
 }
 
-__global__ void k_maxpool3x3s2(int N, int H, int W, int C4, const float* __restrict__ x, float* __restrict__ y) {
+__global__ void __launch_bounds__(256)
+k_maxpool3x3s2(int N, int H, int W, int C4, const float* __restrict__ x, float* __restrict__ y) {
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t total = (size_t)N * Ho * Wo * C4;
-    if (i >= total) return;
-    const int c4 = (int)(i % C4);
-    size_t r = i / C4;
-    const int wo = (int)(r % Wo); r /= Wo;
-    const int ho = (int)(r % Ho);
-    const int n = (int)(r / Ho);
+    const int row = blockIdx.x;
+    const int n = row / Ho, ho = row - n * Ho;
+    const int i = blockIdx.y * blockDim.x + threadIdx.x;
+    if (i >= Wo * C4) return;
+    const int wo = i / C4, c4 = i - wo * C4;
     float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
     for (int dy = 0; dy < 3; ++dy) {
         const int hh = ho * 2 - 1 + dy;
@@ -304,11 +335,11 @@ __global__ void k_maxpool3x3s2(int N, int H, int W, int C4, const float* __restr
         for (int dx = 0; dx < 3; ++dx) {
             const int ww = wo * 2 - 1 + dx;
             if (ww < 0 || ww >= W) continue;
-            const float4 v = __ldg(reinterpret_cast<const float4*>(x) + (((size_t)n * H + hh) * W + ww) * C4 + c4);
+            const float4 v = __ldg(reinterpret_cast<const float4*>(x) + ((size_t)(n * H + hh) * W + ww) * C4 + c4);
             m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
         }
     }
-    reinterpret_cast<float4*>(y)[i] = m;
+    reinterpret_cast<float4*>(y)[(size_t)row * Wo * C4 + i] = m;
 }
 
 __global__ void k_global_avgpool(int N, int HW, int C, const float* __restrict__ x, float* __restrict__ y) {
@@ -467,7 +498,10 @@ extern "C" int danet_iuv_clean_parts(int32_t N, int32_t HW, int32_t Cx, int32_t 
     DANET_CHECK(N >= 0 && HW > 0 && Cx >= 21 && Cy >= 21, "danet_iuv_clean_parts: bad sizes");
     if (N == 0) return 0;
     DANET_CHECK(x && y, "danet_iuv_clean_parts: null pointer");
-    k_iuv_clean_parts<<<cdiv((int64_t)N * HW, 128), 128, 0, (cudaStream_t)s>>>(N, HW, Cx, Cy, x, y, raw_nchw);
+    if (Cx % 4 == 0 && Cy % 4 == 0 && Cx >= 24 && Cy >= 24)
+        k_iuv_clean_parts<true><<<cdiv((int64_t)N * HW, 128), 128, 0, (cudaStream_t)s>>>(N, HW, Cx, Cy, x, y, raw_nchw);
+    else
+        k_iuv_clean_parts<false><<<cdiv((int64_t)N * HW, 128), 128, 0, (cudaStream_t)s>>>(N, HW, Cx, Cy, x, y, raw_nchw);
     DANET_LAUNCH_CHECK();
     return 0;
 }
@@ -489,8 +523,9 @@ extern "C" int danet_stn_sample(int32_t B, int32_t S, int32_t C, const float* xd
     DANET_CHECK(B >= 0 && S > 1 && C > 0 && C % 4 == 0, "danet_stn_sample: bad sizes (C %% 4 must be 0)");
     if (B == 0) return 0;
     DANET_CHECK(xd && theta && crops, "danet_stn_sample: null pointer");
-    const int64_t total = (int64_t)B * 24 * S * S * (C / 4);
-    k_stn_sample<<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)s>>>(B, S, C, xd, theta, align_corners, crops);
+    DANET_CHECK((int64_t)B * 24 * S < (1LL << 31), "danet_stn_sample: batch too large for one launch");
+    const int items = S * (C / 4);
+    k_stn_sample<<<B * 24 * S, items >= 256 ? 256 : (items + 31) / 32 * 32, 0, (cudaStream_t)s>>>(B, S, C, xd, theta, align_corners, crops);
     DANET_LAUNCH_CHECK();
     return 0;
 }
@@ -509,8 +544,8 @@ extern "C" int danet_fuse_sum(int32_t N, int32_t H, int32_t W, int32_t C, int32_
                     "danet_fuse_sum: term %d has bad upsample factor %d for %dx%d", j, f, H, W);
         a.t[j] = terms[j]; a.f[j] = f;
     }
-    const int64_t total = (int64_t)N * H * W * (C / 4);
-    k_fuse_sum<<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)s>>>(N, H, W, C / 4, a, relu, y);
+    DANET_CHECK((int64_t)N * H < (1LL << 31) && (int64_t)W * (C / 4) <= 65535LL * 256, "danet_fuse_sum: tensor too large for one launch");
+    k_fuse_sum<<<dim3(N * H, cdiv(W * (C / 4), 256)), 256, 0, (cudaStream_t)s>>>(N, H, W, C / 4, a, relu, y);
     DANET_LAUNCH_CHECK();
     return 0;
 }
@@ -520,8 +555,8 @@ extern "C" int danet_maxpool3x3s2(int32_t N, int32_t H, int32_t W, int32_t C, co
     if (N == 0) return 0;
     DANET_CHECK(x && y, "danet_maxpool3x3s2: null pointer");
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-    const int64_t total = (int64_t)N * Ho * Wo * (C / 4);
-    k_maxpool3x3s2<<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)s>>>(N, H, W, C / 4, x, y);
+    DANET_CHECK((int64_t)N * Ho < (1LL << 31) && (int64_t)Wo * (C / 4) <= 65535LL * 256, "danet_maxpool3x3s2: tensor too large for one launch");
+    k_maxpool3x3s2<<<dim3(N * Ho, cdiv(Wo * (C / 4), 256)), 256, 0, (cudaStream_t)s>>>(N, H, W, C / 4, x, y);
     DANET_LAUNCH_CHECK();
     return 0;
 }

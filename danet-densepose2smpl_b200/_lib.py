@@ -30,7 +30,7 @@ class RasterDesc(ctypes.Structure):
 
 class ConvDesc(ctypes.Structure):
     _fields_ = [("N", c_int), ("H", c_int), ("W", c_int), ("Cin", c_int), ("Cout", c_int),
-                ("ksize", c_int), ("stride", c_int), ("pad", c_int), ("wsets", c_int), ("relu", c_int)]
+                ("ksize", c_int), ("stride", c_int), ("pad", c_int), ("wsets", c_int), ("relu", c_int), ("flags", c_int)]
 
 
 class GcnParams(ctypes.Structure):

@@ -75,36 +75,46 @@ k_conv_simt(ConvArgs a) {
             rb = __ldg(reinterpret_cast<const float4*>(wg + ((size_t)tap * a.Cin + kc) * a.Cout + co));
     };
 
-    float4 ra, rb;
-    load(0, ra, rb);
-    for (int chunk = 0; chunk < nchunks; ++chunk) {
-        if (a_role) { As[lv * 4 + 0][lp] = ra.x; As[lv * 4 + 1][lp] = ra.y; As[lv * 4 + 2][lp] = ra.z; As[lv * 4 + 3][lp] = ra.w; }
-        if (b_role) *reinterpret_cast<float4*>(&Bs[bk][bv * 4]) = rb;
-        __syncthreads();
-        if (chunk + 1 < nchunks) load(chunk + 1, ra, rb);
+    // kPF chunks of operands are in flight per thread: with one, every 16-channel chunk cost a full L2
+    // round trip (288 chunks x ~0.8 us for the 2x2-pixel 512-channel layers)
+    constexpr int kPF = 4;
+    float4 ra[kPF], rb[kPF];
 #pragma unroll
-        for (int k = 0; k < kKC; ++k) {
-            float am[MT], bm[NTH];
-            if (MT == 4) {
-                const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-                am[0] = av.x; am[1] = av.y; am[MT - 2] = av.z; am[MT - 1] = av.w;
-            } else {
-                const float2 av = *reinterpret_cast<const float2*>(&As[k][ty * 2]);
-                am[0] = av.x; am[1] = av.y;
+    for (int d = 0; d < kPF; ++d)
+        if (d < nchunks) load(d, ra[d], rb[d]);
+    for (int chunk0 = 0; chunk0 < nchunks; chunk0 += kPF) {
+#pragma unroll
+        for (int d = 0; d < kPF; ++d) {
+            const int chunk = chunk0 + d;
+            if (chunk >= nchunks) break;
+            if (a_role) { As[lv * 4 + 0][lp] = ra[d].x; As[lv * 4 + 1][lp] = ra[d].y; As[lv * 4 + 2][lp] = ra[d].z; As[lv * 4 + 3][lp] = ra[d].w; }
+            if (b_role) *reinterpret_cast<float4*>(&Bs[bk][bv * 4]) = rb[d];
+            __syncthreads();
+            if (chunk + kPF < nchunks) load(chunk + kPF, ra[d], rb[d]);
+#pragma unroll
+            for (int k = 0; k < kKC; ++k) {
+                float am[MT], bm[NTH];
+                if (MT == 4) {
+                    const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+                    am[0] = av.x; am[1] = av.y; am[MT - 2] = av.z; am[MT - 1] = av.w;
+                } else {
+                    const float2 av = *reinterpret_cast<const float2*>(&As[k][ty * 2]);
+                    am[0] = av.x; am[1] = av.y;
+                }
+                if (NTH == 4) {
+                    const float4 bv4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+                    bm[0] = bv4.x; bm[1] = bv4.y; bm[NTH - 2] = bv4.z; bm[NTH - 1] = bv4.w;
+                } else {
+                    const float2 bv2 = *reinterpret_cast<const float2*>(&Bs[k][tx * 2]);
+                    bm[0] = bv2.x; bm[1] = bv2.y;
+                }
+#pragma unroll
+                for (int i = 0; i < MT; ++i)
+#pragma unroll
+                    for (int j = 0; j < NTH; ++j) acc[i][j] = fmaf(am[i], bm[j], acc[i][j]);
             }
-            if (NTH == 4) {
-                const float4 bv4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-                bm[0] = bv4.x; bm[1] = bv4.y; bm[NTH - 2] = bv4.z; bm[NTH - 1] = bv4.w;
-            } else {
-                const float2 bv2 = *reinterpret_cast<const float2*>(&Bs[k][tx * 2]);
-                bm[0] = bv2.x; bm[1] = bv2.y;
-            }
-#pragma unroll
-            for (int i = 0; i < MT; ++i)
-#pragma unroll
-                for (int j = 0; j < NTH; ++j) acc[i][j] = fmaf(am[i], bm[j], acc[i][j]);
+            __syncthreads();
         }
-        __syncthreads();
     }
 
     const int co = co0 + tx * NTH;
@@ -151,8 +161,8 @@ int conv_simt_launch(const danet_conv_desc* d, const float* x, const float* w, c
     return 0;
 }
 
-int conv_tc_launch(const danet_conv_desc* d, const float* x, const void* w_packed, const float* bias,
-                   const float* residual, float* y, cudaStream_t stream);   // conv_tc.cu
+int conv_tc_launch(const danet_conv_desc* d, const void* x, const void* w_packed, const float* bias,
+                   const float* residual, void* y, cudaStream_t stream);   // conv_tc.cu
 
 }  // namespace danet
 
@@ -169,12 +179,16 @@ static int check_conv_desc(const danet_conv_desc* d) {
     return 0;
 }
 
-extern "C" int danet_conv2d(const danet_conv_desc* d, int32_t algo, const float* x, const float* w,
-                            const float* bias, const float* residual, float* y, danet_stream_t stream) {
+extern "C" int danet_conv2d(const danet_conv_desc* d, int32_t algo, const void* x, const float* w,
+                            const float* bias, const float* residual, void* y, danet_stream_t stream) {
     if (check_conv_desc(d) != 0) return -1;
     if (d->N == 0) return 0;
     DANET_CHECK(x && w && y, "danet_conv2d: null pointer");
-    if (algo == DANET_CONV_SIMT) return conv_simt_launch(d, x, w, bias, residual, y, (cudaStream_t)stream);
+    DANET_CHECK((d->flags & ~(DANET_CONV_X_F16 | DANET_CONV_Y_F16)) == 0, "danet_conv2d: unknown flags 0x%x", d->flags);
+    if (algo == DANET_CONV_SIMT) {
+        DANET_CHECK(d->flags == 0, "danet_conv2d: fp16 tensors are only taken by the tensor-core path");
+        return conv_simt_launch(d, (const float*)x, w, bias, residual, (float*)y, (cudaStream_t)stream);
+    }
     if (algo == DANET_CONV_TC) {
         DANET_CHECK(danet_conv_tc_supported(d), "danet_conv2d: shape not supported by the tcgen05 path");
         return conv_tc_launch(d, x, (const void*)w, bias, residual, y, (cudaStream_t)stream);

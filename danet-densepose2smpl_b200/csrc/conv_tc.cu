@@ -68,6 +68,7 @@ struct Geom {
     int tmem_cols, ctas_per_sm, b_resident, variant;
     int slabW, nslab, s_pitch, s_out_bytes;   // epilogue transposition buffer: 128 rows x (slabW + 4) floats
     int KS, acc_stages;                  // independent accumulators per tile (K split), TMEM accumulator stages
+    int x_f16, y_f16;                    // activations in / out stored as fp16 (danet_conv_desc.flags)
     long long blocks_per_set;            // packed weight blocks per weight set
     // division-free index math: q = (x * m) >> 40 is exact for x < 2^24, divisor < 2^16 (mdiv())
     unsigned long long m_ntn, m_tw, m_th, m_ws, m_Wp[4];
@@ -87,6 +88,8 @@ static bool make_geom(const danet_conv_desc* d, Geom* g) {
     g->N = d->N; g->H = d->H; g->W = d->W; g->Cin = d->Cin; g->Cout = d->Cout; g->ks = d->ksize;
     g->pad = d->pad; g->stride = d->stride; g->relu = d->relu; g->wsets = d->wsets;
     g->variant = tc_variant();
+    g->x_f16 = (d->flags & DANET_CONV_X_F16) ? 1 : 0; g->y_f16 = (d->flags & DANET_CONV_Y_F16) ? 1 : 0;
+    if ((g->x_f16 && d->Cin % 8 != 0) || (g->y_f16 && d->Cout % 8 != 0)) return false;
     g->KS = 1; g->acc_stages = 2;
     g->Ho = (d->H + 2 * d->pad - d->ksize) / d->stride + 1;
     g->Wo = (d->W + 2 * d->pad - d->ksize) / d->stride + 1;
@@ -323,7 +326,7 @@ __device__ __forceinline__ void decode_tile(const Geom& g, int tile, int& nt, in
 
 struct Args {
     Geom g;
-    const float* x; const float* wpk; const float* bias; const float* res; float* y;
+    const void* x; const float* wpk; const float* bias; const float* res; void* y;   // x / y: fp32, or fp16 when g.x_f16 / g.y_f16
     long long* prof;      // optional [16] cycle counters of CTA 0 (bring-up instrumentation), else NULL
 };
 
@@ -515,7 +518,8 @@ k_conv_tc(const Args a) {
             int nt_, tw, th, img;
             decode_tile(g, tile, nt_, tw, th, img);
             const int h0 = th * kTileH * g.stride - g.pad, w0 = tw * kTileW * g.stride - g.pad;
-            const float* xi = a.x + (size_t)img * HWC * g.Cin + cg * 8;
+            const float* xi = reinterpret_cast<const float*>(a.x) + (size_t)img * HWC * g.Cin + cg * 8;
+            const __half* xi16 = reinterpret_cast<const __half*>(a.x) + (size_t)img * HWC * g.Cin + cg * 8;
             for (int c = 0, u = 0; c < g.nchunks; ++c)
             for (int slot = 0; slot < g.npa; ++slot, ++u) {
                 const int Wp = g.Wp[slot], Hp = g.Hp[slot];
@@ -529,6 +533,25 @@ k_conv_tc(const Args a) {
                 const bool ch_ok = c * g.KCH + cg * 8 < g.Cin;       // channels beyond Cin are zero-filled in smem
                 const bool ch_ok2 = c * g.KCH + cg * 8 + 4 < g.Cin;  // second float4 of the 8-channel chunk
                 const float* xc = xi + c * g.KCH;
+                if (g.x_f16) {
+                    // fp16 activations: every 16-byte piece (8 channels) is one cp.async with zero fill, the
+                    // stage barrier is armed by cp.async.mbarrier.arrive.noinc: no registers, no conversion
+                    const __half* xc16 = xi16 + c * g.KCH;
+                    for (int p = 0; p < npass; ++p) {
+                        if (hh < Hp) {
+                            const int ih = hb + g.stride * hh, iw = wb + g.stride * ww;
+                            const uint32_t dst = a_st + swz((uint32_t)(hh * g.WP + ww) * g.SWB + cg * 16, smask);
+                            const bool ok = ch_ok && ih >= 0 && ih < g.H && iw >= 0 && iw < g.W;
+                            const void* src = ok ? (const void*)(xc16 + ((size_t)ih * g.W + iw) * g.Cin) : a.x;
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16u : 0u) : "memory");
+                        }
+                        ww += dww; hh += dhh;
+                        if (ww >= Wp) { ww -= Wp; hh += 1; }
+                    }
+                    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_a_full + 8 * as) : "memory");
+                    if (++as == g.na_stages) { as = 0; aph ^= 1; }
+                    continue;
+                }
                 // fp32 activations are converted to fp16 (RN, saturating) on the way into shared memory:
                 // half the operand bytes per MAC for the tensor core and twice the K per MMA.  All global
                 // loads of a batch are issued before the first conversion/store.
@@ -582,7 +605,7 @@ k_conv_tc(const Args a) {
         const bool prof_on = PROF && a.prof != nullptr && blockIdx.x == 0 && warp == kWarpEpi && lane == 0;
         long long prof_acc[1] = {0};
         const long long t_start = prof_on ? clock64() : 0;
-        if (!(g.variant & 1)) {
+        {
             // Quad mapping (tcgen05.ld 16x256b): a thread owns tile column ww = lane/4 of the four tile rows
             // 4q..4q+3 and, per 16-column group, channels 2*(lane%4)+{0,1} and +8: the four lanes of a quad
             // read/write one whole 32-byte sector, a warp instruction touches 8 lines instead of 32.  The
@@ -623,7 +646,8 @@ k_conv_tc(const Args a) {
                             const float* v = (k < 2 ? va : vb) + 4 * i + 2 * (k & 1);
                             float2 o = make_float2(v[0] + bb.x + rv[2 * k + i].x, v[1] + bb.y + rv[2 * k + i].y);
                             if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); }
-                            *reinterpret_cast<float2*>(a.y + pix0 + k * rowstep + co) = o;
+                            if (g.y_f16) *reinterpret_cast<uint32_t*>(reinterpret_cast<__half*>(a.y) + pix0 + k * rowstep + co) = pack_h2(o.x, o.y);
+                            else *reinterpret_cast<float2*>(reinterpret_cast<float*>(a.y) + pix0 + k * rowstep + co) = o;
                         }
                     }
                 };
@@ -659,66 +683,6 @@ k_conv_tc(const Args a) {
                 mbar_arrive(bar_acc_empty + 8 * cs);
                 if (++cs == g.acc_stages) { cs = 0; cph ^= 1; }
             }
-        } else {
-        const int m = q * 32 + lane;
-        const int hh = m >> 3, ww = m & 7;
-        for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
-            int nt, tw, th, img;
-            decode_tile(g, tile, nt, tw, th, img);
-            const int oh = th * kTileH + hh, ow = tw * kTileW + ww;
-            const bool valid = oh < g.Ho && ow < g.Wo;
-            const size_t pix = ((size_t)img * g.Ho * g.Wo + (size_t)oh * g.Wo + ow) * g.Cout;
-            const float* bias = a.bias ? a.bias + (size_t)(img - mdiv(img, g.m_ws) * g.wsets) * g.Cout : nullptr;
-            const bool has_res = a.res != nullptr && valid;
-            auto fetch = [&](int grp, float4* rv) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    rv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const int ch = nt * g.NT + grp * 16 + 4 * j;
-                    if (has_res && grp < ngroups && ch < g.Cout) rv[j] = __ldg(reinterpret_cast<const float4*>(a.res + pix + ch));
-                }
-            };
-            auto finish = [&](int grp, const float* v, const float4* rv) {
-                if (!valid) return;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int ch = nt * g.NT + grp * 16 + 4 * j;
-                    if (ch < g.Cout) {
-                        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (bias) bb = __ldg(reinterpret_cast<const float4*>(bias + ch));
-                        float4 o = make_float4(v[4 * j] + bb.x + rv[j].x, v[4 * j + 1] + bb.y + rv[j].y,
-                                               v[4 * j + 2] + bb.z + rv[j].z, v[4 * j + 3] + bb.w + rv[j].w);
-                        if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                        *reinterpret_cast<float4*>(a.y + pix + ch) = o;
-                    }
-                }
-            };
-            float4 r0[4], r1[4], r2[4];
-            fetch(half, r0); fetch(half + 2, r1); fetch(half + 4, r2);
-            { TC_PROF_BEGIN(); mbar_wait_sleep(bar_acc_full + 8 * cs, cph); TC_PROF_END(0); }
-            if (PROF && tl && warp == kWarpEpi && lane == 0 && tile == (int)blockIdx.x) tl[6] = clock64() - t_entry;
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cs * g.NT;
-            for (int grp = half; grp < ngroups; grp += 6) {
-                float v[16];
-                tc_ld16(taddr + grp * 16, v);
-                finish(grp, v, r0);
-                fetch(grp + 6, r0);
-                if (grp + 2 < ngroups) {
-                    tc_ld16(taddr + (grp + 2) * 16, v);
-                    finish(grp + 2, v, r1);
-                    fetch(grp + 8, r1);
-                }
-                if (grp + 4 < ngroups) {
-                    tc_ld16(taddr + (grp + 4) * 16, v);
-                    finish(grp + 4, v, r2);
-                    fetch(grp + 10, r2);
-                }
-            }
-            tc_fence_before();
-            mbar_arrive(bar_acc_empty + 8 * cs);
-            if (++cs == g.acc_stages) { cs = 0; cph ^= 1; }
-        }
         }
         if (prof_on) { a.prof[6] = clock64() - t_start; a.prof[7] = prof_acc[0]; }
         if (PROF && tl && warp == kWarpEpi && lane == 0) tl[7] = clock64() - t_entry;
@@ -769,8 +733,8 @@ __global__ void k_pack(const Geom g, const float* __restrict__ w, __half* __rest
 
 static long long* g_tc_prof = nullptr;
 
-int conv_tc_launch(const danet_conv_desc* d, const float* x, const void* w_packed, const float* bias,
-                   const float* residual, float* y, cudaStream_t stream) {
+int conv_tc_launch(const danet_conv_desc* d, const void* x, const void* w_packed, const float* bias,
+                   const float* residual, void* y, cudaStream_t stream) {
     tc::Args a;
     if (!tc::make_geom(d, &a.g)) { set_error("conv_tc_launch: unsupported shape"); return -1; }
     a.x = x; a.wpk = (const float*)w_packed; a.bias = bias; a.res = residual; a.y = y;

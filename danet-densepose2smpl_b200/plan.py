@@ -26,7 +26,10 @@ class CudaOps(object):
         c = _lib.ConvDesc()
         for k in ("N", "H", "W", "Cin", "Cout", "ksize", "stride", "pad", "wsets", "relu"):
             setattr(c, k, int(d[k]))
+        c.flags = int(d.get("flags", 0))
         return c
+
+    supports_f16 = True      # tensor-core convs take / produce fp16 activation buffers (danet_conv_desc.flags)
 
     def conv_tc_supported(self, d):
         return bool(self.lib.danet_conv_tc_supported(ctypes.byref(self._desc(d))))
@@ -172,7 +175,7 @@ class Plan(object):
     RP = "iuv2smpl.smpl_para_Outs."
 
     def __init__(self, graph, state_dict, B, device, conv_algo="simt", align_corners=False, vis_thresh=0.5,
-                 want_vis=True, ops=None, use_cuda_graph=False):
+                 want_vis=True, ops=None, use_cuda_graph=False, f16_intermediates=True):
         self.g, self.B, self.device = graph, B, torch.device(device)
         self.ops = ops if ops is not None else CudaOps(device)
         self.align_corners, self.vis_thresh, self.want_vis = align_corners, vis_thresh, want_vis
@@ -182,6 +185,7 @@ class Plan(object):
         sd = state_dict
         dev = self.device
         self.steps = []
+        self.f16 = self._f16_tensors() if f16_intermediates else set()
         self._plan_buffers()
         for op in graph.ops:
             kind = op["op"]
@@ -218,6 +222,47 @@ class Plan(object):
         self.use_cuda_graph = use_cuda_graph
         self.static_in = None
 
+    # -- fp16 intermediates -------------------------------------------------------------------
+    def _conv_desc(self, op):
+        x, y = op["x"], op["y"]
+        return dict(N=self.B * x.nmult, H=x.H, W=x.W, Cin=x.Cp, Cout=y.Cp, ksize=op["k"], stride=op["stride"],
+                    pad=op["pad"], wsets=op["groups"], relu=int(op["relu"]))
+
+    def _f16_tensors(self):
+        """Tensors written by a tensor-core conv and read ONLY as the input of tensor-core convs are kept
+        in fp16: that kernel rounds its activations to fp16 (RN) when it stages them, so the values the
+        MMAs see are bit-identical and the tensor costs half the traffic.  Residuals, fuse terms, glue
+        inputs and graph outputs stay fp32."""
+        if self.conv_algo != "tc" or not getattr(self.ops, "supports_f16", False):
+            return set()
+        tc = {}
+        for op in self.g.ops:
+            if op["op"] == "conv":
+                tc[id(op)] = self.ops.conv_tc_supported(self._conv_desc(op))
+        produced_by_tc, bad = set(), set()
+        for op in self.g.ops:
+            if op["op"] == "conv":
+                if tc[id(op)]:
+                    produced_by_tc.add(op["y"].name)
+                else:
+                    bad.add(op["x"].name)
+                if op["res"] is not None:
+                    bad.add(op["res"].name)
+            else:
+                for key in ("x", "hm", "amax", "theta", "gpara"):
+                    t = op.get(key)
+                    if t is not None:
+                        bad.add(t.name)
+                for (t, _f) in op.get("terms", []):
+                    bad.add(t.name)
+        keep = set(t.name for t in self.g.outputs.values())
+        out = set()
+        for name in produced_by_tc - bad - keep:
+            t = self.g.tensors[name]
+            if t.Cp % 8 == 0 and t.dtype == "f32":
+                out.add(name)
+        return out
+
     # -- buffers ------------------------------------------------------------------------------
     def _plan_buffers(self):
         g, B, dev = self.g, self.B, self.device
@@ -251,6 +296,9 @@ class Plan(object):
                 numel = int(np.prod(shape))
                 if t.dtype == "u8":
                     self.buf[name] = torch.empty(shape[:3], dtype=torch.uint8, device=dev)
+                elif name in self.f16:
+                    pool = free.get(("h", numel))
+                    self.buf[name] = pool.pop().view(shape) if pool else torch.empty(shape, dtype=torch.float16, device=dev)
                 else:
                     pool = free.get(numel)
                     if pool and name not in keep:
@@ -262,6 +310,8 @@ class Plan(object):
                 t = self.buf.get(name)
                 if t is not None and t.dtype == torch.float32:
                     free.setdefault(t.numel(), []).append(t)
+                elif t is not None and t.dtype == torch.float16:
+                    free.setdefault(("h", t.numel()), []).append(t)
         seen = {}
         for t in self.buf.values():
             seen[t.untyped_storage().data_ptr()] = t.untyped_storage().nbytes()
@@ -275,10 +325,12 @@ class Plan(object):
         x, y = op["x"], op["y"]
         w, b = pack_conv(sd, op)
         dev = self.device
-        d = dict(N=self.B * x.nmult, H=x.H, W=x.W, Cin=x.Cp, Cout=y.Cp, ksize=op["k"], stride=op["stride"],
-                 pad=op["pad"], wsets=op["groups"], relu=int(op["relu"]))
+        d = self._conv_desc(op)
+        d["flags"] = (1 if x.name in self.f16 else 0) | (2 if y.name in self.f16 else 0)
         w, b = w.to(dev), b.to(dev)
         algo = 0
+        if d["flags"] and not self.ops.conv_tc_supported(d):
+            raise RuntimeError("plan: fp16 tensor on a convolution the tensor-core path does not take: %r" % (d,))
         if self.conv_algo == "tc" and self.ops.conv_tc_supported(d):
             w = self.ops.conv_tc_pack(d, w)
             algo = 1

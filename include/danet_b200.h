@@ -128,13 +128,21 @@ typedef struct {
                                           res_module.py:335-342,500-535 become wsets=24 over the
                                           (batch,part)-flattened image axis)                       */
     int32_t relu;                      /* apply ReLU last                                         */
+    int32_t flags;                     /* tensor-core path only: DANET_CONV_X_F16 / DANET_CONV_Y_F16 --
+                                          x / y are IEEE fp16 NHWC buffers (Cin resp. Cout % 8 == 0).
+                                          The tcgen05 kernel rounds its activations to fp16 (RN) anyway;
+                                          storing an intermediate that only feeds such convolutions in
+                                          fp16 moves that rounding into the producer's epilogue: same
+                                          bits, half the traffic.  residual / bias stay fp32.            */
 } danet_conv_desc;
+#define DANET_CONV_X_F16 1
+#define DANET_CONV_Y_F16 2
 
 /* Weight packing for the SIMT path: w [wsets][ksize*ksize*Cin][Cout] (tap-major, then cin),
  * bias [wsets][Cout] (BN folded by the caller).  residual (or NULL) has the output's shape and is
  * added before the ReLU (res_module.py:40-56,77-97). */
-int danet_conv2d(const danet_conv_desc* d, int32_t algo, const float* x, const float* w,
-                 const float* bias, const float* residual, float* y, danet_stream_t stream);
+int danet_conv2d(const danet_conv_desc* d, int32_t algo, const void* x, const float* w,
+                 const float* bias, const float* residual, void* y, danet_stream_t stream);
 /* bytes / packing helper for the tensor-core path: converts the SIMT layout above into the
  * shared-memory image blocks the tcgen05 kernel bulk-copies (device -> device, once at load). */
 int64_t danet_conv_tc_packed_bytes(const danet_conv_desc* d);

@@ -166,3 +166,49 @@ def test_gcn_pose_head_vs_torch():
     gpc = {k: ([t.to(DEV) for t in v] if isinstance(v, list) else v.to(DEV)) for k, v in gp.items()}
     p = torch.empty(B, 1, 1, 229, device=DEV); ops.gcn_head(gpc, rot.to(DEV), gpara.to(DEV), p)
     assert (p.cpu() - p_ref).abs().max() < 5e-5
+
+
+F16_CASES = [
+    # N, H, W, C1, C2, C3, k, stride
+    (2, 56, 56, 48, 48, 48, 3, 1),
+    (3, 13, 9, 24, 40, 16, 3, 1),          # ragged tiles, narrow channel counts
+    (2, 28, 28, 64, 64, 128, 3, 2),        # fp16 input through the stride-2 parity planes
+    (2, 20, 20, 24, 64, 64, 7, 2),         # limb_net.0 -> conv1 pattern (1x1 then 7x7 stride 2)
+]
+
+
+@pytest.mark.parametrize("case", F16_CASES)
+def test_conv_tc_f16_intermediate_is_bit_identical(case):
+    """y = conv2(conv1(x)): storing the intermediate as fp16 (DANET_CONV_Y_F16 / _X_F16) must give the
+    same bits as the fp32 intermediate, because the kernel rounds its activations to fp16 (RN) either way."""
+    N, H, W, C1, C2, C3, k, s = case
+    ops = _ops()
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(N, H, W, C1, generator=g).to(DEV)
+    k1 = 1 if k == 7 else 3
+    d1 = dict(N=N, H=H, W=W, Cin=C1, Cout=C2, ksize=k1, stride=1, pad=k1 // 2, wsets=1, relu=1)
+    Ho = (H + 2 * (k // 2) - k) // s + 1
+    Wo = (W + 2 * (k // 2) - k) // s + 1
+    d2 = dict(N=N, H=H, W=W, Cin=C2, Cout=C3, ksize=k, stride=s, pad=k // 2, wsets=1, relu=0)
+    w1 = (torch.randn(1, k1 * k1 * C1, C2, generator=g) * 0.1).to(DEV)
+    w2 = (torch.randn(1, k * k * C2, C3, generator=g) * 0.05).to(DEV)
+    b1 = (torch.randn(1, C2, generator=g) * 0.1).to(DEV)
+    b2 = (torch.randn(1, C3, generator=g) * 0.1).to(DEV)
+    res = torch.randn(N, Ho, Wo, C3, generator=g).to(DEV)
+    p1, p2 = ops.conv_tc_pack(d1, w1), ops.conv_tc_pack(d2, w2)
+    # fp32 intermediate
+    t32 = torch.empty(N, H, W, C2, device=DEV)
+    y32 = torch.empty(N, Ho, Wo, C3, device=DEV)
+    ops.conv2d(d1, 1, x, p1, b1, None, t32)
+    ops.conv2d(d2, 1, t32, p2, b2, res, y32)
+    # fp16 intermediate
+    t16 = torch.full((N, H, W, C2), float("nan"), dtype=torch.float16, device=DEV)
+    y16 = torch.empty(N, Ho, Wo, C3, device=DEV)
+    ops.conv2d(dict(d1, flags=2), 1, x, p1, b1, None, t16)
+    ops.conv2d(dict(d2, flags=1), 1, t16, p2, b2, res, y16)
+    torch.cuda.synchronize()
+    assert torch.equal(t16, t32.to(torch.float16))       # same RN rounding as torch
+    assert torch.equal(y16, y32)
+    # the fp32 FMA path refuses fp16 tensors
+    with pytest.raises(RuntimeError):
+        ops.conv2d(dict(d1, flags=2), 0, x, w1, b1, None, t16)

@@ -76,3 +76,17 @@ def test_evaluate_batch_matches_oracle_mpjpe():
     want = lbs.mpjpe_h36m(ref["joints_h36m"], gt.cpu().numpy().astype(np.float64))
     np.testing.assert_allclose(out["mpjpe"].cpu().numpy(), want, atol=1e-5)
     assert out["pred_j14"].shape == (3, 14, 3)
+
+
+def test_f16_intermediates_are_bit_identical():
+    """conv->conv tensors stored in fp16 (danet_conv_desc.flags): the tensor-core kernel rounds its
+    activations to fp16 either way, so the whole forward must not change by a single bit."""
+    img = make_image(2, 100).to(DEV)
+    net_a = build(32, DEV, conv_algo="tc", f16_intermediates=True)
+    net_b = build(32, DEV, conv_algo="tc", f16_intermediates=False)
+    pa = net_a.plan_for(2, torch.device(DEV))
+    assert len(pa.f16) > 20, "expected the first conv of every residual block to be stored in fp16"
+    oa, ob = net_a.infer_net(img), net_b.infer_net(img)
+    assert torch.equal(oa["para"], ob["para"])
+    for x, y in zip(oa["visualization"]["iuv_pred"], ob["visualization"]["iuv_pred"]):
+        assert torch.equal(x, y)

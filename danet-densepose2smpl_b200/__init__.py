@@ -9,3 +9,4 @@ from . import geometry, iuvmap  # noqa: F401
 from .danet import DaNet, build_synthetic_danet  # noqa: F401
 from . import synthetic  # noqa: F401
 from . import parallel, evaluate  # noqa: F401
+from .part_utils import PartRenderer  # noqa: F401

@@ -24,8 +24,11 @@
 //             complete on an mbarrier (no cuTensorMap); small weight sets stay resident in smem.
 //   MMA     : one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N, K=16) and
 //             releases smem stages / publishes accumulators with tcgen05.commit -> mbarrier.
-//   Epilogue: 4 warps read TMEM with tcgen05.ld (32 lanes x 16 columns), add bias (+ residual),
-//             ReLU, and store 16-byte vectors to NHWC global memory.
+//   Epilogue: 8 warps read TMEM with tcgen05.ld.16x256b (a quad of lanes owns one 32-byte sector of a
+//             pixel), add bias (+ residual, prefetched), ReLU, and store fp32 (or fp16 when the
+//             consumer is another tensor-core convolution: danet_conv_desc.flags) NHWC.
+//   Launch  : programmatic dependent launch (griddepcontrol): prologue, weight prefetch and index set-up
+//             overlap the previous kernel's tail; division-free tile decode; parameter warm-up.
 // Every mbarrier wait is bounded (traps instead of hanging the device).
 #include "common.cuh"
 #include <cuda_fp16.h>
@@ -591,12 +594,13 @@ k_conv_tc(const Args a) {
         if (prof_on) { a.prof[4] = clock64() - t_start; a.prof[5] = prof_acc[0]; }
     } else if (warp < kWarpB) {
         // ================= epilogue: TMEM -> bias/residual/ReLU -> global =================
-        // lane = accumulator row (pixel); each of the two warps of a TMEM lane quarter takes every
-        // other 16-column group.  The residual operands of up to THREE groups ahead are held in
-        // registers and the first three are requested BEFORE the accumulator wait: one group
-        // iteration used to cost a full global-load latency (~1.5 us, profiles/r01_tc_role_cycles_v11.log).
-        // (Two smem-staged, fully coalesced variants -- block-wide slabs and warp-private slabs with two
-        //  alternating warp groups -- were both measured SLOWER: profiles/r01_tc_role_cycles_v12_*, _v14_*.)
+        // Each of the two warps of a TMEM lane quarter takes every other 16-column group.  The residual
+        // operands of up to THREE groups ahead are held in registers and the first three are requested
+        // BEFORE the accumulator wait: one group iteration used to cost a full global-load latency
+        // (~1.5 us, profiles/r01_tc_role_cycles_v11.log).  (Two smem-staged, fully coalesced variants --
+        // block-wide slabs and warp-private slabs with two alternating warp groups -- were both measured
+        // SLOWER: profiles/r01_tc_role_cycles_v12_*, _v14_*; the lane = row mapping of the first versions
+        // cost one L1 line per 16 bytes.)
         const int q = warp & 3;                                  // TMEM lane quarter this warp may access
         const int half = (warp - kWarpEpi) >> 2;                 // 0/1: which 16-column groups of the tile this warp owns
         const int ngroups = g.NT / 16;

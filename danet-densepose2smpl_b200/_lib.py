@@ -70,9 +70,9 @@ SIGNATURES = {
     "danet_iuv_clean_global": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                        c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "danet_iuvmap_clean_nchw": (c_int, [c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
-    "danet_iuv_clean_parts": (c_int, [c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p]),
+    "danet_iuv_clean_parts": (c_int, [c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_int, c_p]),
     "danet_stn_params": (c_int, [c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_f, c_int, c_p, c_p, c_p]),
-    "danet_stn_sample": (c_int, [c_int, c_int, c_int, c_p, c_p, c_int, c_p, c_p]),
+    "danet_stn_sample": (c_int, [c_int, c_int, c_int, c_p, c_p, c_int, c_p, c_int, c_p]),
     "danet_gcn_pose_head": (c_int, [c_int, ctypes.POINTER(GcnParams), c_p, c_p, c_p, c_p]),
 }
 

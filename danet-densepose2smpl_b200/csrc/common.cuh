@@ -50,4 +50,13 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// two fp32 -> packed fp16x2 (lo in the lower half), round-to-nearest-even, saturating: the conversion the
+// tensor-core convolution applies to its activations (conv_tc.cu), shared by the kernels that may write
+// fp16 activation buffers for it
+__device__ __forceinline__ uint32_t pack_h2_rn(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
 }  // namespace danet

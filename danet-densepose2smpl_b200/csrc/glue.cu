@@ -1,6 +1,7 @@
 // Memory-bound fp32 glue kernels of the DaNet network half (NHWC activations).
 // Each replaces a chain of small ATen launches in the reference; citations per kernel.
 #include "common.cuh"
+#include <cuda_fp16.h>
 #include <math.h>
 
 namespace danet {
@@ -77,7 +78,7 @@ __global__ void k_iuv_clean_global(int B, int HW, int Chead, int off_u, int off_
 // written as 16-byte vectors when Cx, Cy are multiples of 4 -- they are, the graph pads channels)
 template <bool VEC>
 __global__ void k_iuv_clean_parts(int N, int HW, int Cx, int Cy, const float* __restrict__ x,
-                                  float* __restrict__ y, float* raw) {
+                                  void* __restrict__ yv, float* raw, int y_f16) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)N * HW) return;
     const float* h = x + i * Cx;
@@ -93,7 +94,7 @@ __global__ void k_iuv_clean_parts(int N, int HW, int Cx, int Cy, const float* __
         for (int c = 0; c < 21; ++c) v[c] = h[c];
     }
     const int best = argmax_first(v + 14, 7);
-    float* o = y + i * Cy;
+    float* o = reinterpret_cast<float*>(yv) + i * Cy;                 // fp32 view (unused when y_f16)
     float ov[24];
 #pragma unroll
     for (int c = 0; c < 7; ++c) {
@@ -101,7 +102,14 @@ __global__ void k_iuv_clean_parts(int N, int HW, int Cx, int Cy, const float* __
         ov[c] = oh * v[c]; ov[7 + c] = oh * v[7 + c]; ov[14 + c] = oh;
     }
     ov[21] = ov[22] = ov[23] = 0.0f;
-    if (VEC) {
+    if (VEC && y_f16) {
+        uint4* oh = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(yv) + i * Cy);     // Cy % 8 == 0
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            oh[c] = make_uint4(pack_h2_rn(ov[8 * c], ov[8 * c + 1]), pack_h2_rn(ov[8 * c + 2], ov[8 * c + 3]),
+                               pack_h2_rn(ov[8 * c + 4], ov[8 * c + 5]), pack_h2_rn(ov[8 * c + 6], ov[8 * c + 7]));
+        for (int c = 3; c < Cy / 8; ++c) oh[c] = make_uint4(0u, 0u, 0u, 0u);
+    } else if (VEC) {
 #pragma unroll
         for (int c = 0; c < 6; ++c)
             reinterpret_cast<float4*>(o)[c] = make_float4(ov[4 * c], ov[4 * c + 1], ov[4 * c + 2], ov[4 * c + 3]);
@@ -242,7 +250,7 @@ k_stn_params(int B, int S, int Chm, const float* __restrict__ hm, const uint8_t*
 // per-element 64-bit div/mod chain of the first version cost more than the 16-byte store it fed
 __global__ void __launch_bounds__(256)
 k_stn_sample(int B, int S, int C, const float* __restrict__ xd, const float* __restrict__ theta,
-             int align_corners, float* __restrict__ crops) {
+             int align_corners, void* __restrict__ crops, int out_f16) {
     const int C4 = C >> 2;
     const int bp = blockIdx.x / S, py = blockIdx.x - bp * S;
     const int b = bp / 24;
@@ -260,7 +268,7 @@ k_stn_sample(int B, int S, int C, const float* __restrict__ xd, const float* __r
     const bool y_ok = fy > -2.0f && fy < (float)S + 1.0f;
     const int y0 = y_ok ? (int)fy : 0;
     const float* img = xd + (size_t)b * S * S * C;
-    float4* out = reinterpret_cast<float4*>(crops) + ((size_t)bp * S + py) * S * C4;
+    const size_t obase = ((size_t)bp * S + py) * S * C4;            // in 4-channel groups
     const int items = S * C4;
     for (int i = threadIdx.x; i < items; i += blockDim.x) {
         const int px = i / C4, c4 = i - px * C4;
@@ -290,29 +298,31 @@ k_stn_sample(int B, int S, int C, const float* __restrict__ xd, const float* __r
                     acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
                 }
         }
-        out[i] = acc;
+        if (out_f16) reinterpret_cast<uint2*>(crops)[obase + i] = make_uint2(pack_h2_rn(acc.x, acc.y), pack_h2_rn(acc.z, acc.w));
+        else reinterpret_cast<float4*>(crops)[obase + i] = acc;
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // HRNet fuse (hr_module.py:161-179): y = relu(sum_j nearest_up(t_j))
 // ------------------------------------------------------------------------------------------
-struct FuseArgs { const float* t[4]; int f[4]; int n; };
+struct FuseArgs { const float* t[4]; int f[4]; int n; };      // f = log2 of the upsample factor (1,2,4,8 -> 0..3)
 
 // grid = (n*H + h, chunks of a row): no per-element 64-bit division
 __global__ void __launch_bounds__(256)
-k_fuse_sum(int N, int H, int W, int C4, FuseArgs a, int relu, float* __restrict__ y) {
+k_fuse_sum(int N, int H, int W, int C4, unsigned long long mC4, FuseArgs a, int relu, float* __restrict__ y) {
     const int row = blockIdx.x;
     const int n = row / H, h = row - n * H;
     const int i = blockIdx.y * blockDim.x + threadIdx.x;
     if (i >= W * C4) return;
-    const int w = i / C4, c4 = i - w * C4;
+    const int w = (int)(((unsigned long long)(unsigned)i * mC4) >> 40), c4 = i - w * C4;     // i / C4, exact (i < 2^24)
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int j = 0; j < a.n; ++j) {
-        const int f = a.f[j];
-        const int hh = H / f, ww = W / f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (j >= a.n) break;
+        const int sh = a.f[j];
         const float4 v = __ldg(reinterpret_cast<const float4*>(a.t[j]) +
-                               ((size_t)(n * hh + h / f) * ww + w / f) * C4 + c4);
+                               ((size_t)(n * (H >> sh) + (h >> sh)) * (W >> sh) + (w >> sh)) * C4 + c4);
         if (j == 0) acc = v;
         else { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
     }
@@ -493,15 +503,16 @@ extern "C" int danet_iuv_clean_global(int32_t B, int32_t HW, int32_t Chead, int3
     return 0;
 }
 
-extern "C" int danet_iuv_clean_parts(int32_t N, int32_t HW, int32_t Cx, int32_t Cy, const float* x, float* y,
-                                     float* raw_nchw, danet_stream_t s) {
+extern "C" int danet_iuv_clean_parts(int32_t N, int32_t HW, int32_t Cx, int32_t Cy, const float* x, void* y,
+                                     float* raw_nchw, int32_t y_f16, danet_stream_t s) {
     DANET_CHECK(N >= 0 && HW > 0 && Cx >= 21 && Cy >= 21, "danet_iuv_clean_parts: bad sizes");
     if (N == 0) return 0;
     DANET_CHECK(x && y, "danet_iuv_clean_parts: null pointer");
+    DANET_CHECK(!y_f16 || (Cx % 4 == 0 && Cx >= 24 && Cy % 8 == 0 && Cy >= 24), "danet_iuv_clean_parts: fp16 output needs Cx %% 4 == 0, Cy %% 8 == 0");
     if (Cx % 4 == 0 && Cy % 4 == 0 && Cx >= 24 && Cy >= 24)
-        k_iuv_clean_parts<true><<<cdiv((int64_t)N * HW, 128), 128, 0, (cudaStream_t)s>>>(N, HW, Cx, Cy, x, y, raw_nchw);
+        k_iuv_clean_parts<true><<<cdiv((int64_t)N * HW, 128), 128, 0, (cudaStream_t)s>>>(N, HW, Cx, Cy, x, y, raw_nchw, y_f16);
     else
-        k_iuv_clean_parts<false><<<cdiv((int64_t)N * HW, 128), 128, 0, (cudaStream_t)s>>>(N, HW, Cx, Cy, x, y, raw_nchw);
+        k_iuv_clean_parts<false><<<cdiv((int64_t)N * HW, 128), 128, 0, (cudaStream_t)s>>>(N, HW, Cx, Cy, x, y, raw_nchw, 0);
     DANET_LAUNCH_CHECK();
     return 0;
 }
@@ -519,13 +530,13 @@ extern "C" int danet_stn_params(int32_t B, int32_t S, int32_t Chm, const float* 
 }
 
 extern "C" int danet_stn_sample(int32_t B, int32_t S, int32_t C, const float* xd, const float* theta,
-                                int32_t align_corners, float* crops, danet_stream_t s) {
+                                int32_t align_corners, void* crops, int32_t out_f16, danet_stream_t s) {
     DANET_CHECK(B >= 0 && S > 1 && C > 0 && C % 4 == 0, "danet_stn_sample: bad sizes (C %% 4 must be 0)");
     if (B == 0) return 0;
     DANET_CHECK(xd && theta && crops, "danet_stn_sample: null pointer");
     DANET_CHECK((int64_t)B * 24 * S < (1LL << 31), "danet_stn_sample: batch too large for one launch");
     const int items = S * (C / 4);
-    k_stn_sample<<<B * 24 * S, items >= 256 ? 256 : (items + 31) / 32 * 32, 0, (cudaStream_t)s>>>(B, S, C, xd, theta, align_corners, crops);
+    k_stn_sample<<<B * 24 * S, items >= 256 ? 256 : (items + 31) / 32 * 32, 0, (cudaStream_t)s>>>(B, S, C, xd, theta, align_corners, crops, out_f16);
     DANET_LAUNCH_CHECK();
     return 0;
 }
@@ -542,10 +553,10 @@ extern "C" int danet_fuse_sum(int32_t N, int32_t H, int32_t W, int32_t C, int32_
         const int f = factors[j];
         DANET_CHECK(terms[j] && (f == 1 || f == 2 || f == 4 || f == 8) && H % f == 0 && W % f == 0,
                     "danet_fuse_sum: term %d has bad upsample factor %d for %dx%d", j, f, H, W);
-        a.t[j] = terms[j]; a.f[j] = f;
+        a.t[j] = terms[j]; a.f[j] = f == 1 ? 0 : (f == 2 ? 1 : (f == 4 ? 2 : 3));
     }
-    DANET_CHECK((int64_t)N * H < (1LL << 31) && (int64_t)W * (C / 4) <= 65535LL * 256, "danet_fuse_sum: tensor too large for one launch");
-    k_fuse_sum<<<dim3(N * H, cdiv(W * (C / 4), 256)), 256, 0, (cudaStream_t)s>>>(N, H, W, C / 4, a, relu, y);
+    DANET_CHECK((int64_t)N * H < (1LL << 31) && (int64_t)W * (C / 4) < (1 << 24) && C / 4 < (1 << 16), "danet_fuse_sum: tensor too large for one launch");
+    k_fuse_sum<<<dim3(N * H, cdiv(W * (C / 4), 256)), 256, 0, (cudaStream_t)s>>>(N, H, W, C / 4, (1ull << 40) / (unsigned long long)(C / 4) + 1ull, a, relu, y);
     DANET_LAUNCH_CHECK();
     return 0;
 }

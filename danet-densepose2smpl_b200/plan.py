@@ -83,7 +83,7 @@ class CudaOps(object):
     def clean_parts(self, x, y, raw):
         N, H, W, Cx = x.shape
         _lib.check(self.lib.danet_iuv_clean_parts(N, H * W, Cx, y.shape[-1], _lib.ptr(x), _lib.ptr(y), _lib.ptr(raw),
-                                                  _lib.stream_ptr()), "iuv_clean_parts")
+                                                  int(y.dtype == torch.float16), _lib.stream_ptr()), "iuv_clean_parts")
 
     def stn_params(self, hm, amax, ratio, offset, vis_thresh, align_corners, centers, theta):
         B, S, _, Chm = hm.shape
@@ -94,7 +94,8 @@ class CudaOps(object):
     def stn_sample(self, xd, theta, align_corners, crops):
         B, S, _, C = xd.shape
         _lib.check(self.lib.danet_stn_sample(B, S, C, _lib.ptr(xd), _lib.ptr(theta), int(align_corners),
-                                             _lib.ptr(crops), _lib.stream_ptr()), "stn_sample")
+                                             _lib.ptr(crops), int(crops.dtype == torch.float16), _lib.stream_ptr()),
+                   "stn_sample")
 
     def gcn_head(self, gp, rot_feats, gpara, para):
         B = para.shape[0]
@@ -222,6 +223,12 @@ class Plan(object):
         self.use_cuda_graph = use_cuda_graph
         self.static_in = None
 
+    # tensors callers read after run() (infer_net, tests): never recycled, never fp16
+    KEEP = ("para", "centers", "theta", "amax", "global_para", "rot_feats", "heads", "hm", "body_iuv")
+
+    def _keep(self):
+        return set(self.g.outputs[k].name for k in self.KEEP if k in self.g.outputs)
+
     # -- fp16 intermediates -------------------------------------------------------------------
     def _conv_desc(self, op):
         x, y = op["x"], op["y"]
@@ -249,13 +256,15 @@ class Plan(object):
                 if op["res"] is not None:
                     bad.add(op["res"].name)
             else:
+                if op["op"] in ("stn_sample", "clean_parts"):
+                    produced_by_tc.add(op["y"].name)       # these two glue kernels can write fp16 as well
                 for key in ("x", "hm", "amax", "theta", "gpara"):
                     t = op.get(key)
                     if t is not None:
                         bad.add(t.name)
                 for (t, _f) in op.get("terms", []):
                     bad.add(t.name)
-        keep = set(t.name for t in self.g.outputs.values())
+        keep = self._keep()
         out = set()
         for name in produced_by_tc - bad - keep:
             t = self.g.tensors[name]
@@ -279,7 +288,7 @@ class Plan(object):
                 t = op.get(key)
                 if t is not None and t.name not in produced:
                     produced[t.name] = idx
-        keep = set(t.name for t in g.outputs.values())
+        keep = self._keep()
         free = {}
         self.buf = {}
         release_at = {}

@@ -189,8 +189,10 @@ int danet_iuvmap_clean_nchw(int32_t B, int32_t C, int32_t Ca, int32_t HW, const 
  * first 21 channels (N = batch*24) -> y [N,HW,Cy>=21] cleaned (pad channels zeroed); optional raw
  * copy in the reference's
  * layout part_iuv_pred [N,21,HW] (iuv_estimator.py:208-211). */
-int danet_iuv_clean_parts(int32_t N, int32_t HW, int32_t Cx, int32_t Cy, const float* x, float* y,
-                          float* raw_nchw, danet_stream_t stream);
+/* y_f16 != 0: y is an fp16 [N,HW,Cy] buffer (Cy % 8 == 0) for a tensor-core convolution, same RN
+ * rounding that convolution would apply to the fp32 values (see danet_conv_desc.flags). */
+int danet_iuv_clean_parts(int32_t N, int32_t HW, int32_t Cx, int32_t Cy, const float* x, void* y,
+                          float* raw_nchw, int32_t y_f16, danet_stream_t stream);
 /* iuv_estimator.py:137-140,176-184,262-301: soft-argmax centres of 10*hm, part visibility,
  * affine thetas.  hm [B,HW,Chm] (24 heatmap channels first), index_argmax [B,HW] ->
  * centers [B,24,2] (x,y in [-1,1]), theta [B,24,3] = (scale, cx, cy).
@@ -201,8 +203,9 @@ int danet_stn_params(int32_t B, int32_t S, int32_t Chm, const float* hm, const u
                      int32_t align_corners, float* centers, float* theta, danet_stream_t stream);
 /* iuv_estimator.py:193-204: 24x affine_grid + grid_sample (bilinear, zeros) of xd [B,S,S,C]
  * -> crops [B*24,S,S,C] (image index b*24+part) */
+/* out_f16 != 0: crops is an fp16 buffer (consumed only by the grouped tensor-core convolution). */
 int danet_stn_sample(int32_t B, int32_t S, int32_t C, const float* xd, const float* theta,
-                     int32_t align_corners, float* crops, danet_stream_t stream);
+                     int32_t align_corners, void* crops, int32_t out_f16, danet_stream_t stream);
 
 /* smpl_regressor.py:858-895 + GCN.py:29-92 + geometry.py:47-61: r2p_gcn -> refine_gcn(+res) ->
  * p2r_gcn -> grouped 1x1 pose head + mean_pose -> rot6d_to_rotmat; also concatenates

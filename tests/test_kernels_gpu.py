@@ -131,6 +131,9 @@ def test_clean_and_stn_kernels_vs_torch():
     y, raw = torch.empty(B * 24, S, S, 24, device=DEV), torch.empty(B * 24, 21, S, S, device=DEV)
     ops.clean_parts(x.to(DEV), y, raw)
     assert torch.equal(y.cpu(), y_r) and torch.equal(raw.cpu(), raw_r)
+    y16 = torch.full((B * 24, S, S, 24), float("nan"), dtype=torch.float16, device=DEV)      # fp16 output option
+    ops.clean_parts(x.to(DEV), y16, None)
+    assert torch.equal(y16.cpu(), y_r.to(torch.float16))
     # stn params + sampling, both align_corners conventions
     hm = torch.randn(B, S, S, 24, generator=g) * 0.3
     ratio, offset = torch.rand(24, generator=g) + 0.5, torch.rand(24, generator=g) * 0.2
@@ -144,6 +147,9 @@ def test_clean_and_stn_kernels_vs_torch():
         crops_r = torch.empty(B * 24, S, S, C); ref.stn_sample(xd, th_r, ac, crops_r)
         crops = torch.empty(B * 24, S, S, C, device=DEV); ops.stn_sample(xd.to(DEV), th_r.to(DEV), ac, crops)
         assert (crops.cpu() - crops_r).abs().max() < 2e-4
+        crops16 = torch.full((B * 24, S, S, C), float("nan"), dtype=torch.float16, device=DEV)
+        ops.stn_sample(xd.to(DEV), th_r.to(DEV), ac, crops16)
+        assert torch.equal(crops16, crops.to(torch.float16))           # same values, RN-rounded
 
 
 def test_gcn_pose_head_vs_torch():

@@ -69,7 +69,7 @@ struct Geom {
     int a_stage_bytes, b_stage_bytes, tap_bytes, nb_stages, na_stages;
     int smem_bytes;
     int tmem_cols, ctas_per_sm, b_resident, variant;
-    int slabW, nslab, s_pitch, s_out_bytes;   // epilogue transposition buffer: 128 rows x (slabW + 4) floats
+    int bias_smem;                       // bytes of the [wsets][Cout] bias staged in shared memory (0: read from global)
     int KS, acc_stages;                  // independent accumulators per tile (K split), TMEM accumulator stages
     int x_f16, y_f16;                    // activations in / out stored as fp16 (danet_conv_desc.flags)
     long long blocks_per_set;            // packed weight blocks per weight set
@@ -128,11 +128,8 @@ static bool make_geom(const danet_conv_desc* d, Geom* g) {
     while (cols < g->acc_stages * g->KS * g->NT) cols *= 2;
     g->tmem_cols = cols;
     const int taps = d->ksize * d->ksize;
-    g->slabW = g->NT < 64 ? g->NT : 64;
-    g->nslab = (g->NT + g->slabW - 1) / g->slabW;
-    g->s_pitch = g->slabW + 4;
-    g->s_out_bytes = 128 * g->s_pitch * 4;
-    const int fixed = 512 + 1024;
+    g->bias_smem = (long long)d->wsets * d->Cout * 4 <= 8192 ? (d->wsets * d->Cout * 4 + 15) / 16 * 16 : 0;
+    const int fixed = 512 + 1024 + g->bias_smem;      // barriers + 1024-byte alignment slack + staged bias
     // widest swizzle whose double-buffered halo + a minimal weight pipeline fits
     bool ok = false;
     for (int swb = 128; swb >= 32 && !ok; swb /= 2) {
@@ -349,7 +346,7 @@ k_conv_tc(const Args a) {
     const uint32_t bar_a_full = sBar, bar_a_empty = sBar + 24, bar_acc_full = sBar + 48, bar_acc_empty = sBar + 64;
     const uint32_t bar_b_full = sBar + 80, bar_b_empty = sBar + 80 + 8 * kMaxBStages;
     const uint32_t tmem_slot_addr = sBar + 80 + 16 * kMaxBStages;       // 80 + 256 + 4 <= 512
-    const uint32_t sOut = sBar + 512;                                   // epilogue transposition buffer (16-byte aligned)
+    const uint32_t sBias = sBar + 512;                                  // [wsets][Cout] fp32 bias (when g.bias_smem)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // the kernel parameters (about 1 KB, new for every launch) are read through the constant cache:
@@ -368,6 +365,9 @@ k_conv_tc(const Args a) {
         for (int i = 0; i < g.nb_stages; ++i) { mbar_init(bar_b_full + 8 * i, 1); mbar_init(bar_b_empty + 8 * i, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (g.bias_smem && a.bias)                                          // weights: independent of the previous kernel
+        for (int i = threadIdx.x; i < g.wsets * g.Cout; i += kThreads)
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(sBias + 4 * i), "f"(__ldg(a.bias + i)) : "memory");
     if (warp == kWarpMma) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot_addr), "r"((uint32_t)g.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -624,7 +624,8 @@ k_conv_tc(const Args a) {
                 const size_t rowstep = (size_t)g.Wo * g.Cout;
                 const int nrows = ow < g.Wo ? min(4, g.Ho - oh0) : 0;        // valid tile rows of this thread (<= 0: none)
                 const int chlim = g.Cout - nt * g.NT - cq;                   // channel offsets below this are real
-                const float* bias = a.bias ? a.bias + (size_t)(img - mdiv(img, g.m_ws) * g.wsets) * g.Cout + nt * g.NT + cq : nullptr;
+                const int boff = (img - mdiv(img, g.m_ws) * g.wsets) * g.Cout + nt * g.NT + cq;   // first channel of this thread
+                const float* bias = a.bias ? a.bias + boff : nullptr;
                 const bool has_res = a.res != nullptr;
                 auto fetch = [&](int grp, float2* rv) {
 #pragma unroll
@@ -643,7 +644,12 @@ k_conv_tc(const Args a) {
                         const int co = grp * 16 + 8 * i;
                         if (co >= chlim) continue;
                         float2 bb = make_float2(0.f, 0.f);
-                        if (bias) bb = __ldg(reinterpret_cast<const float2*>(bias + co));
+                        // a global bias load sat in the dependent chain of every group: an L2 round trip each
+                        // time its line had been evicted (4.3K cycles per 128 x 64 tile in the 1x1 24->64 layer)
+                        if (bias) {
+                            if (g.bias_smem) asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(bb.x), "=f"(bb.y) : "r"(sBias + 4 * (boff + co)));
+                            else bb = __ldg(reinterpret_cast<const float2*>(bias + co));
+                        }
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             if (k >= nrows) continue;

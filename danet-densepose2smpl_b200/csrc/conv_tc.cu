@@ -333,7 +333,9 @@ struct Args {
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <bool PROF>
+// PROF: bring-up instrumentation; RES: a residual tensor is added in the epilogue (compile-time so that the
+// layers without one carry none of the prefetch code)
+template <bool PROF, bool RES>
 __global__ void __launch_bounds__(kThreads, 1)
 k_conv_tc(const Args a) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -608,6 +610,7 @@ k_conv_tc(const Args a) {
         pdl_wait();                                              // residual reads / output writes
         const bool prof_on = PROF && a.prof != nullptr && blockIdx.x == 0 && warp == kWarpEpi && lane == 0;
         long long prof_acc[1] = {0};
+        long long ph[6] = {0, 0, 0, 0, 0, 0};      // PROF: decode+addresses, residual fetch issue, acc wait, tcgen05.ld, finish (math+stores), arrive
         const long long t_start = prof_on ? clock64() : 0;
         {
             // Quad mapping (tcgen05.ld 16x256b): a thread owns tile column ww = lane/4 of the four tile rows
@@ -617,6 +620,7 @@ k_conv_tc(const Args a) {
             // the epilogue: 8-9 us for one exposed 128 x 192 tile (per-CTA timeline in profiles/).
             const int wwq = lane >> 2, cq = 2 * (lane & 3);
             for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+                long long tp = prof_on ? clock64() : 0;
                 int nt, tw, th, img;
                 decode_tile(g, tile, nt, tw, th, img);
                 const int ow = tw * kTileW + wwq, oh0 = th * kTileH + 4 * q;
@@ -626,15 +630,18 @@ k_conv_tc(const Args a) {
                 const int chlim = g.Cout - nt * g.NT - cq;                   // channel offsets below this are real
                 const int boff = (img - mdiv(img, g.m_ws) * g.wsets) * g.Cout + nt * g.NT + cq;   // first channel of this thread
                 const float* bias = a.bias ? a.bias + boff : nullptr;
-                const bool has_res = a.res != nullptr;
+                constexpr bool has_res = RES;
+                // (without a residual the whole prefetch is skipped: its predicate arithmetic alone cost ~500 cycles
+                //  per tile, profiles/r01_tc_epilogue_phases.txt)
                 auto fetch = [&](int grp, float2* rv) {
+                    if (!has_res) return;
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
 #pragma unroll
                         for (int i = 0; i < 2; ++i) {
                             rv[2 * k + i] = make_float2(0.f, 0.f);
                             const int co = grp * 16 + 8 * i;
-                            if (has_res && grp < ngroups && k < nrows && co < chlim)
+                            if (grp < ngroups && k < nrows && co < chlim)
                                 rv[2 * k + i] = __ldg(reinterpret_cast<const float2*>(a.res + pix0 + k * rowstep + co));
                         }
                 };
@@ -662,8 +669,13 @@ k_conv_tc(const Args a) {
                     }
                 };
                 float2 r0[8], r1[8], r2[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) r0[i] = r1[i] = r2[i] = make_float2(0.f, 0.f);
+                if (prof_on) { const long long t = clock64(); ph[0] += t - tp; tp = t; }
                 fetch(half, r0); fetch(half + 2, r1); fetch(half + 4, r2);
+                if (prof_on) { const long long t = clock64(); ph[1] += t - tp; tp = t; }
                 { TC_PROF_BEGIN(); mbar_wait_sleep(bar_acc_full + 8 * cs, cph); TC_PROF_END(0); }
+                if (prof_on) { const long long t = clock64(); ph[2] += t - tp; tp = t; }
                 if (PROF && tl && warp == kWarpEpi && lane == 0 && tile == (int)blockIdx.x) tl[6] = clock64() - t_entry;
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cs * g.NT;
@@ -672,14 +684,18 @@ k_conv_tc(const Args a) {
                     tc_ld16x256_x2_nowait(taddr + grp * 16, va);
                     tc_ld16x256_x2_nowait(taddr + (16u << 16) + grp * 16, vb);
                     tc_wait_ld();
+                    if (prof_on) { const long long t = clock64(); ph[3] += t - tp; tp = t; }
                     finish(grp, va, vb, r0);
                     fetch(grp + 6, r0);
+                    if (prof_on) { const long long t = clock64(); ph[4] += t - tp; tp = t; }
                     if (grp + 2 < ngroups) {
                         tc_ld16x256_x2_nowait(taddr + (grp + 2) * 16, va);
                         tc_ld16x256_x2_nowait(taddr + (16u << 16) + (grp + 2) * 16, vb);
                         tc_wait_ld();
+                        if (prof_on) { const long long t = clock64(); ph[3] += t - tp; tp = t; }
                         finish(grp + 2, va, vb, r1);
                         fetch(grp + 8, r1);
+                        if (prof_on) { const long long t = clock64(); ph[4] += t - tp; tp = t; }
                     }
                     if (grp + 4 < ngroups) {
                         tc_ld16x256_x2_nowait(taddr + (grp + 4) * 16, va);
@@ -692,8 +708,10 @@ k_conv_tc(const Args a) {
                 tc_fence_before();
                 mbar_arrive(bar_acc_empty + 8 * cs);
                 if (++cs == g.acc_stages) { cs = 0; cph ^= 1; }
+                if (prof_on) { const long long t = clock64(); ph[5] += t - tp; tp = t; }
             }
         }
+        if (prof_on) for (int i = 0; i < 6; ++i) a.prof[8 + i] = ph[i];
         if (prof_on) { a.prof[6] = clock64() - t_start; a.prof[7] = prof_acc[0]; }
         if (PROF && tl && warp == kWarpEpi && lane == 0) tl[7] = clock64() - t_entry;
     }
@@ -756,8 +774,10 @@ int conv_tc_launch(const danet_conv_desc* d, const void* x, const void* w_packed
         int dev = 0;
         DANET_CUDA(cudaGetDevice(&dev));
         DANET_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-        DANET_CUDA(cudaFuncSetAttribute(tc::k_conv_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-        DANET_CUDA(cudaFuncSetAttribute(tc::k_conv_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        DANET_CUDA(cudaFuncSetAttribute(tc::k_conv_tc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        DANET_CUDA(cudaFuncSetAttribute(tc::k_conv_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        DANET_CUDA(cudaFuncSetAttribute(tc::k_conv_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        DANET_CUDA(cudaFuncSetAttribute(tc::k_conv_tc<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
         const char* e = getenv("DANET_TC_PDL");
         use_pdl = !(e && atoi(e) == 0);
         attr_set = true;
@@ -771,8 +791,13 @@ int conv_tc_launch(const danet_conv_desc* d, const void* x, const void* w_packed
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = use_pdl ? 1 : 0;
-    if (a.prof) { DANET_CUDA(cudaLaunchKernelEx(&cfg, tc::k_conv_tc<true>, a)); }
-    else { DANET_CUDA(cudaLaunchKernelEx(&cfg, tc::k_conv_tc<false>, a)); }
+    if (a.prof) {
+        if (a.res) { DANET_CUDA(cudaLaunchKernelEx(&cfg, tc::k_conv_tc<true, true>, a)); }
+        else { DANET_CUDA(cudaLaunchKernelEx(&cfg, tc::k_conv_tc<true, false>, a)); }
+    } else {
+        if (a.res) { DANET_CUDA(cudaLaunchKernelEx(&cfg, tc::k_conv_tc<false, true>, a)); }
+        else { DANET_CUDA(cudaLaunchKernelEx(&cfg, tc::k_conv_tc<false, false>, a)); }
+    }
     DANET_LAUNCH_CHECK();
     return 0;
 }

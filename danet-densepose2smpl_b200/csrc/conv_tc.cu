@@ -679,6 +679,25 @@ k_conv_tc(const Args a) {
                 if (PROF && tl && warp == kWarpEpi && lane == 0 && tile == (int)blockIdx.x) tl[6] = clock64() - t_entry;
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cs * g.NT;
+                if constexpr (!RES) {
+                    // no residual registers to carry: TMEM loads of TWO column groups are in flight before the one
+                    // tcgen05.wait::ld (the wait covers every outstanding load anyway)
+                    for (int grp = half; grp < ngroups; grp += 4) {
+                        float va[8], vb[8], wa[8], wb[8];
+                        const bool two = grp + 2 < ngroups;
+                        tc_ld16x256_x2_nowait(taddr + grp * 16, va);
+                        tc_ld16x256_x2_nowait(taddr + (16u << 16) + grp * 16, vb);
+                        if (two) {
+                            tc_ld16x256_x2_nowait(taddr + (grp + 2) * 16, wa);
+                            tc_ld16x256_x2_nowait(taddr + (16u << 16) + (grp + 2) * 16, wb);
+                        }
+                        tc_wait_ld();
+                        if (prof_on) { const long long t = clock64(); ph[3] += t - tp; tp = t; }
+                        finish(grp, va, vb, r0);
+                        if (two) finish(grp + 2, wa, wb, r0);
+                        if (prof_on) { const long long t = clock64(); ph[4] += t - tp; tp = t; }
+                    }
+                } else
                 for (int grp = half; grp < ngroups; grp += 6) {
                     float va[8], vb[8];
                     tc_ld16x256_x2_nowait(taddr + grp * 16, va);

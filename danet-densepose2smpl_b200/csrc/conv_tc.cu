@@ -179,6 +179,7 @@ static bool make_geom(const danet_conv_desc* d, Geom* g) {
     if (g->smem_bytes < 120 * 1024) g->smem_bytes = 120 * 1024;       // one CTA per SM (TMEM budget)
     g->blocks_per_set = (long long)g->ntn * nblk;
     if (g->total_tiles >= (1 << 24) || g->wsets >= (1 << 16)) return false;
+    if ((long long)d->N * g->Ho * g->Wo * d->Cout >= (1LL << 31) || (long long)d->H * d->W * d->Cin >= (1LL << 31)) return false;   // 32-bit element offsets
     g->m_ntn = magic40(g->ntn); g->m_tw = magic40(g->tiles_w); g->m_th = magic40(g->tiles_h); g->m_ws = magic40(g->wsets);
     {
         const int ppt = kNumProducers / g->CGT;
@@ -547,7 +548,7 @@ k_conv_tc(const Args a) {
                             const int ih = hb + g.stride * hh, iw = wb + g.stride * ww;
                             const uint32_t dst = a_st + swz((uint32_t)(hh * g.WP + ww) * g.SWB + cg * 16, smask);
                             const bool ok = ch_ok && ih >= 0 && ih < g.H && iw >= 0 && iw < g.W;
-                            const void* src = ok ? (const void*)(xc16 + ((size_t)ih * g.W + iw) * g.Cin) : a.x;
+                            const void* src = ok ? (const void*)(xc16 + (uint32_t)((ih * g.W + iw) * g.Cin)) : a.x;
                             asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16u : 0u) : "memory");
                         }
                         ww += dww; hh += dhh;
@@ -571,7 +572,7 @@ k_conv_tc(const Args a) {
                             const int ih = hb + g.stride * hh, iw = wb + g.stride * ww;
                             dst[q] = a_st + swz((uint32_t)(hh * g.WP + ww) * g.SWB + cg * 16, smask);
                             if (ch_ok && ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) {
-                                const float4* src = reinterpret_cast<const float4*>(xc + ((size_t)ih * g.W + iw) * g.Cin);
+                                const float4* src = reinterpret_cast<const float4*>(xc + (uint32_t)((ih * g.W + iw) * g.Cin));
                                 v0[q] = __ldg(src);
                                 if (ch_ok2) v1[q] = __ldg(src + 1);
                             }
@@ -624,8 +625,9 @@ k_conv_tc(const Args a) {
                 int nt, tw, th, img;
                 decode_tile(g, tile, nt, tw, th, img);
                 const int ow = tw * kTileW + wwq, oh0 = th * kTileH + 4 * q;
-                const size_t pix0 = ((size_t)img * g.Ho * g.Wo + (size_t)oh0 * g.Wo + ow) * g.Cout + nt * g.NT + cq;
-                const size_t rowstep = (size_t)g.Wo * g.Cout;
+                // element offsets fit 32 bits (make_geom refuses tensors of 2^31 elements or more)
+                const uint32_t pix0 = ((uint32_t)(img * g.Ho + oh0) * g.Wo + ow) * g.Cout + nt * g.NT + cq;
+                const uint32_t rowstep = (uint32_t)(g.Wo * g.Cout);
                 const int nrows = ow < g.Wo ? min(4, g.Ho - oh0) : 0;        // valid tile rows of this thread (<= 0: none)
                 const int chlim = g.Cout - nt * g.NT - cq;                   // channel offsets below this are real
                 const int boff = (img - mdiv(img, g.m_ws) * g.wsets) * g.Cout + nt * g.NT + cq;   // first channel of this thread

@@ -23,7 +23,11 @@ def main():
         if "k_conv_tc" in kn or "k_conv_simt" in kn:
             e = d.setdefault(int(x["ID"]), {"k": "tc" if "k_conv_tc" in kn else "simt"})
             e[x["Metric Name"]] = float(x["Metric Value"].replace(",", ""))
-    ids = sorted(d)[-len(convs):]
+    # launch order = graph order; the capture may end mid-step, so take the SECOND complete step
+    # (the first one is the warm-up) when there is one, else the first
+    allids = sorted(d)
+    start = len(convs) if len(allids) >= 2 * len(convs) else 0
+    ids = allids[start:start + len(convs)]
     agg = collections.OrderedDict()
     tot = 0.0
     for i, op in zip(ids, convs):

@@ -18,7 +18,8 @@ for (N, H, W, Cin, Cout, k, st) in cases:
     y = torch.empty(N, Ho, Wo, Cout, device=DEV)
     wp = ops.conv_tc_pack(d, w)
     prof = torch.zeros(16 + 16 * 160, dtype=torch.int64, device=DEV)
-    ops.lib.danet_conv_tc_set_profile_buffer(ctypes.c_void_p(prof.data_ptr()))
+    if not os.environ.get("TC_NOPROF"):          # TC_NOPROF=1: plain instantiation (for ncu captures)
+        ops.lib.danet_conv_tc_set_profile_buffer(ctypes.c_void_p(prof.data_ptr()))
     for _ in range(2):
         ops.conv2d(d, 1, x, wp, b, res, y)
     torch.cuda.synchronize()

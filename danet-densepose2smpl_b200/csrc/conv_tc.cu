@@ -47,8 +47,6 @@ constexpr int kNumEpi = 256;             // two epilogue warps per TMEM lane qua
 constexpr int kNumProducers = 256;
 constexpr int kMaxBStages = 16;
 constexpr int kSmemBudget = 214 * 1024;  // one CTA per SM (227 KB max - static)
-constexpr int kSmemHalf = 100 * 1024;    // two CTAs per SM when everything fits
-constexpr bool kAllowTwoCtas = false;    // needs <= 73 registers/thread (currently 113): off
 
 struct Geom {
     int N, H, W, Cin, Cout, ks, pad, stride, relu, wsets;
@@ -127,7 +125,6 @@ static bool make_geom(const danet_conv_desc* d, Geom* g) {
     int cols = 32;
     while (cols < g->acc_stages * g->KS * g->NT) cols *= 2;
     g->tmem_cols = cols;
-    const int taps = d->ksize * d->ksize;
     g->bias_smem = (long long)d->wsets * d->Cout * 4 <= 8192 ? (d->wsets * d->Cout * 4 + 15) / 16 * 16 : 0;
     const int fixed = 512 + 1024 + g->bias_smem;      // barriers + 1024-byte alignment slack + staged bias
     // widest swizzle whose double-buffered halo + a minimal weight pipeline fits
@@ -158,7 +155,6 @@ static bool make_geom(const danet_conv_desc* d, Geom* g) {
             g->tapidx[a][k] = (g->par_py[a] + d->stride * ti) * d->ksize + (g->par_px[a] + d->stride * tj);
         }
     }
-    (void)taps;
     const int nblk = g->nchunks * g->bpc;
     g->na_stages = 2;
     g->b_resident = 0; g->ctas_per_sm = 1;
@@ -248,7 +244,7 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
@@ -259,27 +255,6 @@ __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
     return pred != 0;
-}
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, float* v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr) : "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 // 16 lanes x 256 bits, twice (columns +0..7 and +8..15): thread t receives, for i = 0/1,
 // r[4i], r[4i+1] = row t/4, columns 8i + 2*(t%4) + {0,1};  r[4i+2], r[4i+3] = row t/4 + 8, same columns
@@ -298,11 +273,6 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
     uint32_t r;
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));   // d = {hi -> upper, lo -> lower}
     return r;
-}
-__device__ __forceinline__ float to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
 }
 // K-major swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1).
 // layout_type: SWIZZLE_128B = 2, SWIZZLE_64B = 4, SWIZZLE_32B = 6; LBO is unused for swizzled K-major.
@@ -381,7 +351,6 @@ k_conv_tc(const Args a) {
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot_addr));
 
-    const int taps = g.ks * g.ks;
     const int HWC = g.H * g.W;
     pdl_launch_dependents();            // the next launch may fill SMs as our CTAs retire
     if (PROF && tl && threadIdx.x == 0) tl[2] = clock64() - t_entry;
@@ -458,30 +427,30 @@ k_conv_tc(const Args a) {
                             if (kv == 4) {
                                 for (int tt = 0; tt < ntk; ++tt) {
                                     const uint64_t ad = ad_st + (uint32_t)g.tapoff16[slot][k0 + tt];
-                                    tc_mma_tf32(d_base, ad, bd, idesc, acc);
-                                    tc_mma_tf32(d_base, ad + 2, bd + 2, idesc, 1u);
-                                    tc_mma_tf32(d_base, ad + 4, bd + 4, idesc, 1u);
-                                    tc_mma_tf32(d_base, ad + 6, bd + 6, idesc, 1u);
+                                    tc_mma_f16(d_base, ad, bd, idesc, acc);
+                                    tc_mma_f16(d_base, ad + 2, bd + 2, idesc, 1u);
+                                    tc_mma_f16(d_base, ad + 4, bd + 4, idesc, 1u);
+                                    tc_mma_f16(d_base, ad + 6, bd + 6, idesc, 1u);
                                     acc = 1; bd += tap16;
                                 }
                             } else if (kv == 3) {
                                 for (int tt = 0; tt < ntk; ++tt) {
                                     const uint64_t ad = ad_st + (uint32_t)g.tapoff16[slot][k0 + tt];
-                                    tc_mma_tf32(d_base, ad, bd, idesc, acc);
-                                    tc_mma_tf32(d_base, ad + 2, bd + 2, idesc, 1u);
-                                    tc_mma_tf32(d_base, ad + 4, bd + 4, idesc, 1u);
+                                    tc_mma_f16(d_base, ad, bd, idesc, acc);
+                                    tc_mma_f16(d_base, ad + 2, bd + 2, idesc, 1u);
+                                    tc_mma_f16(d_base, ad + 4, bd + 4, idesc, 1u);
                                     acc = 1; bd += tap16;
                                 }
                             } else if (kv == 2) {
                                 for (int tt = 0; tt < ntk; ++tt) {
                                     const uint64_t ad = ad_st + (uint32_t)g.tapoff16[slot][k0 + tt];
-                                    tc_mma_tf32(d_base, ad, bd, idesc, acc);
-                                    tc_mma_tf32(d_base, ad + 2, bd + 2, idesc, 1u);
+                                    tc_mma_f16(d_base, ad, bd, idesc, acc);
+                                    tc_mma_f16(d_base, ad + 2, bd + 2, idesc, 1u);
                                     acc = 1; bd += tap16;
                                 }
                             } else {
                                 for (int tt = 0; tt < ntk; ++tt) {
-                                    tc_mma_tf32(d_base, ad_st + (uint32_t)g.tapoff16[slot][k0 + tt], bd, idesc, acc);
+                                    tc_mma_f16(d_base, ad_st + (uint32_t)g.tapoff16[slot][k0 + tt], bd, idesc, acc);
                                     acc = 1; bd += tap16;
                                 }
                             }
@@ -506,13 +475,12 @@ k_conv_tc(const Args a) {
             }
         }
     } else if (warp < kWarpEpi) {
-        // ================= A producers: halo tile -> smem (no-swizzle K-major) =================
+        // ================= A producers: halo tile -> smem (swizzled K-major rows) =================
         // thread <-> (channel group cg, pixel slot); pixels advance by a fixed step per pass so the
         // halo coordinates are updated incrementally (no divisions in the loop); every pass's
         // global load is issued before the first shared store (one latency exposure per 8 passes).
         const int pt = threadIdx.x;                             // 0..255
         const int cg = pt & (g.CGT - 1);                         // 16-byte chunk (8 fp16 channels) within the row
-        const int ppt = kNumProducers / g.CGT;                   // pixels per pass
         const int px0 = pt / g.CGT;
         const uint32_t smask = g.SWB == 128 ? 7u : (g.SWB == 64 ? 3u : 1u);
         int as = 0; uint32_t aph = 0;

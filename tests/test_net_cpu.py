@@ -80,3 +80,48 @@ def test_pretrained_flag_needs_files():
                          smpl_model=synthetic.make_smpl_model(0), dp_mesh=synthetic.make_dp_mesh(0))
     with pytest.raises(ValueError):
         danet_b200.DaNet(None, "/nonexistent/smpl_mean_params.npz", pretrained=False)
+
+
+def test_f16_tensor_selection_rules():
+    """plan._f16_tensors (host logic): only tensors written by a tensor-core conv (or the two glue kernels that
+    can write fp16) and read exclusively as the INPUT of tensor-core convs may be stored in fp16."""
+    from danet_b200 import netgraph as ng
+    from danet_b200.plan import Plan
+
+    class FakeOps(object):
+        supports_f16 = True
+
+        def conv_tc_supported(self, d):
+            return d["H"] >= 4 and d["W"] >= 4          # what the tcgen05 kernel declines: tiny maps
+
+    g = ng.danet_graph(48)
+    plan = Plan.__new__(Plan)
+    plan.g, plan.B, plan.conv_algo, plan.ops = g, 2, "tc", FakeOps()
+    f16 = plan._f16_tensors()
+    assert len(f16) > 100
+    readers, writers = {}, {}
+    for op in g.ops:
+        for key in ("x", "res", "hm", "amax", "theta", "gpara"):
+            t = op.get(key)
+            if t is not None:
+                readers.setdefault(t.name, []).append((op, key))
+        for (t, _f) in op.get("terms", []):
+            readers.setdefault(t.name, []).append((op, "term"))
+        if op.get("y") is not None:
+            writers[op["y"].name] = op
+    keep = plan._keep()
+    for name in f16:
+        t = g.tensors[name]
+        assert t.Cp % 8 == 0 and name not in keep
+        w = writers[name]
+        assert w["op"] in ("conv", "stn_sample", "clean_parts")
+        for (op, key) in readers[name]:
+            assert op["op"] == "conv" and key == "x", (name, op["op"], key)     # never a residual / fuse / glue input
+            assert FakeOps().conv_tc_supported(plan._conv_desc(op))
+    # the big limb-branch tensors are in: crops (stn_sample -> grouped conv) and limb_net.0 -> conv1
+    assert g.outputs["part_iuv"].name in f16
+    crops = [op["y"].name for op in g.ops if op["op"] == "stn_sample"][0]
+    assert crops in f16
+    # nothing is selected on the exact fp32 path
+    plan.conv_algo = "simt"
+    assert plan._f16_tensors() == set()

@@ -616,6 +616,41 @@ k_conv_tc(const Args a) {
                         }
                 };
                 auto finish = [&](int grp, const float* va, const float* vb, const float2* rv) {
+                    if (g.y_f16) {
+                        // fp16 output: the two 8-column blocks of the group are paired up inside the quad (one
+                        // shuffle with the neighbour lane per row): even lanes store 4 halves of block 0, odd lanes
+                        // 4 halves of block 1 -- 8-byte stores, half the store instructions and L1 lines of 4-byte ones.
+                        // Cout % 8 == 0 here, so a block is valid or not for the whole quad (no divergence at the shuffle).
+                        const bool odd = lane & 1;
+                        const int cw = g.Cout - nt * g.NT;                       // channels of this N tile that exist
+                        uint32_t pk[2][4];
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const int co = grp * 16 + 8 * i;
+                            float2 bb = make_float2(0.f, 0.f);
+                            if (bias && co < cw) {
+                                if (g.bias_smem) asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(bb.x), "=f"(bb.y) : "r"(sBias + 4 * (boff + co)));
+                                else bb = __ldg(reinterpret_cast<const float2*>(bias + co));
+                            }
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float* v = (k < 2 ? va : vb) + 4 * i + 2 * (k & 1);
+                                float2 o = make_float2(v[0] + bb.x + rv[2 * k + i].x, v[1] + bb.y + rv[2 * k + i].y);
+                                if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); }
+                                pk[i][k] = pack_h2(o.x, o.y);
+                            }
+                        }
+                        const int col = grp * 16 + (odd ? 8 : 0);               // first column of the block this lane stores
+                        const bool blk_ok = col < cw;
+                        __half* yrow = reinterpret_cast<__half*>(a.y) + (pix0 - cq) + col + (odd ? cq - 2 : cq);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint32_t recv = __shfl_xor_sync(0xffffffffu, odd ? pk[0][k] : pk[1][k], 1);
+                            const uint32_t lo = odd ? recv : pk[0][k], hi = odd ? pk[1][k] : recv;
+                            if (blk_ok && k < nrows) *reinterpret_cast<uint2*>(yrow + k * rowstep) = make_uint2(lo, hi);
+                        }
+                        return;
+                    }
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
                         const int co = grp * 16 + 8 * i;
@@ -633,8 +668,7 @@ k_conv_tc(const Args a) {
                             const float* v = (k < 2 ? va : vb) + 4 * i + 2 * (k & 1);
                             float2 o = make_float2(v[0] + bb.x + rv[2 * k + i].x, v[1] + bb.y + rv[2 * k + i].y);
                             if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); }
-                            if (g.y_f16) *reinterpret_cast<uint32_t*>(reinterpret_cast<__half*>(a.y) + pix0 + k * rowstep + co) = pack_h2(o.x, o.y);
-                            else *reinterpret_cast<float2*>(reinterpret_cast<float*>(a.y) + pix0 + k * rowstep + co) = o;
+                            *reinterpret_cast<float2*>(reinterpret_cast<float*>(a.y) + pix0 + k * rowstep + co) = o;
                         }
                     }
                 };

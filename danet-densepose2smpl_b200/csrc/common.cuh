@@ -50,6 +50,16 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// cudaFuncSetAttribute is per device: true the first time the calling thread's current device is seen by this
+// call site (`mask` is the site's static bit set, one bit per device ordinal; -1 on error)
+inline int first_use_on_current_device(unsigned long long* mask) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+    const bool first = !((*mask >> dev) & 1ull);
+    *mask |= 1ull << dev;
+    return first ? 1 : 0;
+}
+
 // two fp32 -> packed fp16x2 (lo in the lower half), round-to-nearest-even, saturating: the conversion the
 // tensor-core convolution applies to its activations (conv_tc.cu), shared by the kernels that may write
 // fp16 activation buffers for it

@@ -790,22 +790,22 @@ int conv_tc_launch(const danet_conv_desc* d, const void* x, const void* w_packed
     if (!tc::make_geom(d, &a.g)) { set_error("conv_tc_launch: unsupported shape"); return -1; }
     a.x = x; a.wpk = (const float*)w_packed; a.bias = bias; a.res = residual; a.y = y;
     a.prof = g_tc_prof;
-    static int sm_count = 0;
-    static bool attr_set = false;
+    static int sm_count_of[64];
+    static unsigned long long attr_devs = 0;
     static bool use_pdl = true;
-    if (!attr_set) {
-        int dev = 0;
-        DANET_CUDA(cudaGetDevice(&dev));
-        DANET_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    int dev = 0;
+    DANET_CUDA(cudaGetDevice(&dev));
+    DANET_CHECK(dev >= 0 && dev < 64, "conv_tc_launch: device ordinal %d out of range", dev);
+    if (first_use_on_current_device(&attr_devs) != 0) {          // function attributes are per device
+        DANET_CUDA(cudaDeviceGetAttribute(&sm_count_of[dev], cudaDevAttrMultiProcessorCount, dev));
         DANET_CUDA(cudaFuncSetAttribute(tc::k_conv_tc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
         DANET_CUDA(cudaFuncSetAttribute(tc::k_conv_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
         DANET_CUDA(cudaFuncSetAttribute(tc::k_conv_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
         DANET_CUDA(cudaFuncSetAttribute(tc::k_conv_tc<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
         const char* e = getenv("DANET_TC_PDL");
         use_pdl = !(e && atoi(e) == 0);
-        attr_set = true;
     }
-    const int cap = sm_count * a.g.ctas_per_sm;
+    const int cap = sm_count_of[dev] * a.g.ctas_per_sm;
     a.g.variant = tc::tc_variant();
     const int grid = a.g.total_tiles < cap ? a.g.total_tiles : cap;
     cudaLaunchConfig_t cfg = {};

@@ -610,11 +610,9 @@ extern "C" int danet_gcn_pose_head(int32_t B, const danet_gcn_params* p, const f
     DANET_CHECK(g.din[0] == 128 && g.dout[0] == 128 && g.dout[3] == 128 && g.din[4] == 128 && g.dout[4] == 128,
                 "danet_gcn_pose_head: expected 128-d r2p / refine-out / p2r features");
     const size_t smem = (size_t)(2 * 24 * kGcnMaxF + 24 * 128 + 576 + 144) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_devs = 0;
+    if (first_use_on_current_device(&attr_devs) != 0)
         DANET_CUDA(cudaFuncSetAttribute(k_gcn_pose_head, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
     k_gcn_pose_head<<<B, kGcnThreads, smem, (cudaStream_t)s>>>(B, g, rot_feats, global_para, para);
     DANET_LAUNCH_CHECK();
     return 0;

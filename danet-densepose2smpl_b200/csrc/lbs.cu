@@ -596,11 +596,10 @@ extern "C" int danet_smpl_forward(danet_smpl_t h, int32_t B, const float* betas,
     const size_t smem = (size_t)nb * (kPF + kJ * 12 + kTileC + kMaxBetas) * sizeof(float);
 #define DANET_LBS_LAUNCH(NBV)                                                                       \
     do {                                                                                            \
-        static bool attr_set = false;                                                               \
-        if (!attr_set) {                                                                            \
+        static unsigned long long attr_devs = 0;                                                    \
+        if (first_use_on_current_device(&attr_devs) != 0) {                                         \
             DANET_CUDA(cudaFuncSetAttribute(k_smpl_verts<NBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                             (int)((size_t)NBV * (kPF + kJ * 12 + kTileC + kMaxBetas) * sizeof(float)))); \
-            attr_set = true;                                                                        \
         }                                                                                           \
         k_smpl_verts<NBV><<<grid, kTileV, smem, stream>>>(B, betas, pf, A, m, verts, partials);     \
     } while (0)

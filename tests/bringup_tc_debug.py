@@ -1,4 +1,4 @@
-"""Bring-up harness for the tcgen05 conv kernel: small isolating cases first, dumps for offline analysis."""
+"""Bring-up harness for the tcgen05 conv kernel (TEST INFRASTRUCTURE: checks against oracle/net_ops.py): small isolating cases first, dumps for offline analysis.  Run as `python tests/bringup_tc_debug.py` on a GPU box."""
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np

@@ -3,7 +3,7 @@ import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import danet_b200
-from oracle import synth
+from danet_b200 import synthetic as synth
 
 dev = torch.device("cuda:0")
 model = synth.make_smpl_model(0)

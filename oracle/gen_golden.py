@@ -1,7 +1,7 @@
 """Generates tests/golden/*.npz by running the REFERENCE'S OWN Python code (imported from
 /root/reference with the shims in oracle/ref_import.py).  Run in this container only:
 
-    python -m oracle.gen_golden [geometry] [iuvmap] [net]
+    python -m oracle.gen_golden [geometry] [iuvmap] [part_utils] [net]
 
 The vectors pin the oracle restatements (oracle/lbs.py geometry helpers) and the CUDA kernels."""
 import os
@@ -57,16 +57,41 @@ def gen_iuvmap(ns):
     print("iuvmap.npz written")
 
 
+def gen_part_utils(ns):
+    """utils/part_utils.py:27-36 (PartRenderer.get_parts) and utils/iuvmap.py:41-70 (iuv_map2img, no-roi branch)."""
+    torch = ns.torch
+    sys.modules['neural_renderer'].Renderer = None
+    import importlib
+    part_utils = importlib.import_module("utils.part_utils")
+    g = torch.Generator().manual_seed(99)
+    pr = object.__new__(part_utils.PartRenderer)                 # the constructor needs a GPU and data files
+    pr.cube_parts = torch.randint(0, 7, (100, 100, 100), generator=g).float()
+    parts = (torch.randint(0, 100, (2, 3, 16, 16), generator=g).float() + 0.5) / 100.0
+    mask = (torch.rand(2, 16, 16, generator=g) > 0.4).float()
+    out = pr.get_parts(parts.clone(), mask.clone())
+    U, V, I = (torch.randn(2, 25, 12, 12, generator=g) for _ in range(3))
+    A = torch.randn(2, 15, 12, 12, generator=g)
+    torch.Tensor.get_device = lambda self: -1 if not self.is_cuda else self.device.index
+    img = ns.iuvmap.iuv_map2img(U, V, I)
+    img_a = ns.iuvmap.iuv_map2img(U, V, I, A)
+    np.savez_compressed(os.path.join(GOLD, "part_utils.npz"), cube=pr.cube_parts.numpy(), parts=parts.numpy(),
+                        mask=mask.numpy(), out=out.numpy(), U=U.numpy(), V=V.numpy(), I=I.numpy(), A=A.numpy(),
+                        img=img.numpy(), img_a=img_a.numpy())
+    print("part_utils.npz written")
+
+
 def main():
     sys.path.insert(0, ROOT)
     from oracle import ref_import
-    what = sys.argv[1:] or ["geometry", "iuvmap", "net"]
+    what = sys.argv[1:] or ["geometry", "iuvmap", "part_utils", "net"]
     ns = ref_import.load(48)
     os.makedirs(GOLD, exist_ok=True)
     if "geometry" in what:
         gen_geometry(ns)
     if "iuvmap" in what:
         gen_iuvmap(ns)
+    if "part_utils" in what:
+        gen_part_utils(ns)
     if "net" in what:
         from oracle import gen_golden_net
         gen_golden_net.main(ns)

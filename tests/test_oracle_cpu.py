@@ -132,3 +132,22 @@ def test_product_does_not_import_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
+
+
+def test_get_parts_and_iuv_map2img_match_reference_golden():
+    """PartRenderer.get_parts (utils/part_utils.py:27-36) and iuv_map2img (utils/iuvmap.py:41-70): host-side
+    tensor code of the SURVEY 8f rows, pinned against outputs of the reference functions themselves
+    (tests/golden/part_utils.npz, made by `python -m oracle.gen_golden part_utils`)."""
+    import os
+    import torch
+    from danet_b200.part_utils import PartRenderer
+    from danet_b200.iuvmap import iuv_map2img
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "part_utils.npz"))
+    faces = np.array([[0, 1, 2], [1, 2, 3]])
+    pr = PartRenderer(faces=faces, textures=np.zeros((2, 3), np.float32), cube_parts=g["cube"], num_smpl_verts=4)
+    out = pr.get_parts(torch.from_numpy(g["parts"]), torch.from_numpy(g["mask"]))
+    assert out.dtype == torch.int64
+    np.testing.assert_array_equal(out.numpy(), g["out"])
+    U, V, I, A = (torch.from_numpy(g[k]) for k in ("U", "V", "I", "A"))
+    np.testing.assert_array_equal(iuv_map2img(U, V, I).numpy(), g["img"])
+    np.testing.assert_array_equal(iuv_map2img(U, V, I, A).numpy(), g["img_a"])

@@ -190,7 +190,7 @@ def run_b200_arm(args):
         dist.init_process_group("nccl", device_id=dev)
     B, W = args.batch, args.width
     net = danet_b200.build_synthetic_danet(width=W, seed=0, device=dev, conv_algo=args.conv,
-                                           use_cuda_graph=not args.no_graph)
+                                           use_cuda_graph=not args.no_graph, gemm_2x2=not args.no_gemm_2x2)
     smpl, rend = net.iuv2smpl.smpl, net.iuv_renderer
     nrot = 4                                          # 4 x 38.5 MB input batches > 126 MB L2
     g = torch.Generator().manual_seed(1234 + rank)
@@ -446,6 +446,8 @@ def main():
     ap.add_argument("--conv", default="auto", choices=["auto", "tc", "simt"])
     ap.add_argument("--cpu-batch", type=int, default=4)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--gemm-2x2", action="store_true", help="(default now) 2x2-pixel 3x3 layers as dense products on the tensor-core path")
+    ap.add_argument("--no-gemm-2x2", action="store_true", help="keep the 2x2-pixel 3x3 layers on the fp32 FMA kernel")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

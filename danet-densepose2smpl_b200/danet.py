@@ -90,7 +90,7 @@ class DaNet(nn.Module):
 
     def __init__(self, options, smpl_mean_params, pretrained=True, width=None, smpl_model=None, dp_mesh=None,
                  conv_algo="auto", legacy_align_corners=False, cfg=None, use_cuda_graph=False, want_vis=True,
-                 f16_intermediates=True):
+                 f16_intermediates=True, gemm_2x2=True):
         super().__init__()
         self.options = options
         self.cfg = dict(DEFAULT_CFG)
@@ -101,6 +101,7 @@ class DaNet(nn.Module):
         self.legacy_align_corners = legacy_align_corners
         self.use_cuda_graph = use_cuda_graph
         self.f16_intermediates = f16_intermediates   # tensor-core path: conv->conv tensors stored as fp16 (same bits at the MMA)
+        self.gemm_2x2 = gemm_2x2                     # tensor-core path: 2x2-pixel 3x3 layers as one dense product (batches that are multiples of 8, >= 32)
         self.want_vis = want_vis
         self.graph = ng.danet_graph(self.width, self.cfg["INIMG_SIZE"])
         mean_params = load_mean_params(smpl_mean_params)
@@ -156,7 +157,8 @@ class DaNet(nn.Module):
             self._plans[key] = Plan(self.graph, sd, B, device, conv_algo=self._algo(),
                                     align_corners=self.legacy_align_corners,
                                     vis_thresh=self.cfg["STN_PART_VIS_SCORE"], want_vis=self.want_vis, ops=ops,
-                                    use_cuda_graph=self.use_cuda_graph, f16_intermediates=self.f16_intermediates)
+                                    use_cuda_graph=self.use_cuda_graph, f16_intermediates=self.f16_intermediates,
+                                    gemm_2x2=self.gemm_2x2)
         return self._plans[key]
 
     # -- inference ------------------------------------------------------------------------------

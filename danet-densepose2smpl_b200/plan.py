@@ -143,6 +143,23 @@ def pack_conv(sd, op):
     return wp.reshape(G, k * k * cin_p, cout_p).contiguous(), bp.contiguous()
 
 
+def conv2x2_as_gemm(w, b, cin, cout):
+    """A 3x3 / stride 1 / pad 1 convolution on 2x2-pixel maps touches every input pixel from every output
+    pixel (|dy|,|dx| <= 1 always), so it IS a dense matrix product: x viewed as [images, 4*cin] times
+    W' [4*cin, 4*cout] with W'[(iy,ix,ci), (oy,ox,co)] = w[ky=iy-oy+1, kx=ix-ox+1, ci, co]  (no padding taps:
+    16 of the 36 (tap, pixel) pairs of the direct form multiply zeros).  NHWC memory of x / y / residual is
+    already [image][(y,x,c)], so nothing moves; the images become the pixels of one 1x1 convolution.
+    w [1][9*cin][cout] (SIMT layout), b [1][cout] -> (w' [1][4*cin][4*cout], b' [1][4*cout])."""
+    w9 = w.reshape(3, 3, cin, cout)
+    out = torch.zeros(2, 2, cin, 2, 2, cout, dtype=w.dtype)
+    for iy in range(2):
+        for ix in range(2):
+            for oy in range(2):
+                for ox in range(2):
+                    out[iy, ix, :, oy, ox, :] = w9[iy - oy + 1, ix - ox + 1]
+    return out.reshape(1, 4 * cin, 4 * cout).contiguous(), b.reshape(1, cout).repeat(1, 4).contiguous()
+
+
 def refine_adjacency(sd, rp):
     """normalize_undigraph(I_n + A_mask * relu(edge_importance)) (smpl_regressor.py:870-871,
     utils/graph.py:232-261) -- parameter-only, so evaluated once per weight load."""
@@ -176,11 +193,12 @@ class Plan(object):
     RP = "iuv2smpl.smpl_para_Outs."
 
     def __init__(self, graph, state_dict, B, device, conv_algo="simt", align_corners=False, vis_thresh=0.5,
-                 want_vis=True, ops=None, use_cuda_graph=False, f16_intermediates=True):
+                 want_vis=True, ops=None, use_cuda_graph=False, f16_intermediates=True, gemm_2x2=False):
         self.g, self.B, self.device = graph, B, torch.device(device)
         self.ops = ops if ops is not None else CudaOps(device)
         self.align_corners, self.vis_thresh, self.want_vis = align_corners, vis_thresh, want_vis
         self.conv_algo = conv_algo
+        self.gemm_2x2 = gemm_2x2          # DaNet passes True; validated by tests/test_kernels_gpu.py, test_net_gpu.py
         self.n_launch = 0
         self.n_tc = 0
         sd = state_dict
@@ -336,6 +354,15 @@ class Plan(object):
         dev = self.device
         d = self._conv_desc(op)
         d["flags"] = (1 if x.name in self.f16 else 0) | (2 if y.name in self.f16 else 0)
+        if (self.gemm_2x2 and self.conv_algo == "tc" and d["ksize"] == 3 and d["stride"] == 1 and d["pad"] == 1 and
+                d["H"] == 2 and d["W"] == 2 and d["wsets"] == 1 and d["N"] % 8 == 0 and d["N"] >= 32):
+            # the ResNet tail's 2x2-pixel layers as one dense product on the tensor-core path (see
+            # conv2x2_as_gemm); the images become an (N/8) x 8 pixel map of a 1x1 convolution
+            d2 = dict(N=1, H=d["N"] // 8, W=8, Cin=4 * d["Cin"], Cout=4 * d["Cout"], ksize=1, stride=1, pad=0,
+                      wsets=1, relu=d["relu"], flags=0)
+            if self.ops.conv_tc_supported(d2):
+                w, b = conv2x2_as_gemm(w, b, d["Cin"], d["Cout"])
+                d = d2
         w, b = w.to(dev), b.to(dev)
         algo = 0
         if d["flags"] and not self.ops.conv_tc_supported(d):

@@ -218,3 +218,27 @@ def test_conv_tc_f16_intermediate_is_bit_identical(case):
     # the fp32 FMA path refuses fp16 tensors
     with pytest.raises(RuntimeError):
         ops.conv2d(dict(d1, flags=2), 0, x, w1, b1, None, t16)
+
+
+def test_conv2x2_as_gemm_on_the_tensor_core_path():
+    """plan.conv2x2_as_gemm: the ResNet tail's 3x3 convolutions on 2x2-pixel maps as ONE dense product through the
+    tcgen05 kernel (images = pixels of a 1x1 convolution, nothing moves in memory) vs the exact fp32 kernel."""
+    from danet_b200.plan import conv2x2_as_gemm
+    ops = _ops()
+    g = torch.Generator().manual_seed(21)
+    N, C = 64, 512
+    x = torch.randn(N, 2, 2, C, generator=g).to(DEV)
+    w = (torch.randn(1, 9 * C, C, generator=g) * 0.02)
+    b = torch.randn(1, C, generator=g) * 0.1
+    res = torch.randn(N, 2, 2, C, generator=g).to(DEV)
+    d = dict(N=N, H=2, W=2, Cin=C, Cout=C, ksize=3, stride=1, pad=1, wsets=1, relu=1)
+    y_ref = torch.empty(N, 2, 2, C, device=DEV)
+    ops.conv2d(d, 0, x, w.to(DEV), b.to(DEV), res, y_ref)
+    d2 = dict(N=1, H=N // 8, W=8, Cin=4 * C, Cout=4 * C, ksize=1, stride=1, pad=0, wsets=1, relu=1)
+    assert ops.conv_tc_supported(d2)
+    w2, b2 = conv2x2_as_gemm(w, b, C, C)
+    y = torch.full((N, 2, 2, C), float("nan"), device=DEV)
+    ops.conv2d(d2, 1, x, ops.conv_tc_pack(d2, w2.to(DEV)), b2.to(DEV), res, y)
+    torch.cuda.synchronize()
+    err = (y - y_ref).abs().max().item() / y_ref.abs().max().item()
+    assert err < 8e-3, err

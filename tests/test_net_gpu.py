@@ -90,3 +90,15 @@ def test_f16_intermediates_are_bit_identical():
     assert torch.equal(oa["para"], ob["para"])
     for x, y in zip(oa["visualization"]["iuv_pred"], ob["visualization"]["iuv_pred"]):
         assert torch.equal(x, y)
+
+
+def test_gemm_2x2_option_matches_fma_path():
+    """DaNet(gemm_2x2=True, the default): body_net's 2x2-pixel layers go through the tensor-core kernel as dense products
+    (needs a batch that is a multiple of 8, >= 32); same parameters within the tensor-core tolerance."""
+    img = make_image(32, 100).to(DEV)
+    net_a = build(32, DEV, conv_algo="tc", gemm_2x2=True)
+    net_b = build(32, DEV, conv_algo="tc", gemm_2x2=False)
+    pa, pb = net_a.plan_for(32, torch.device(DEV)), net_b.plan_for(32, torch.device(DEV))
+    assert pa.n_tc == pb.n_tc + 3                      # the three layer4 convolutions of body_net moved over
+    oa, ob = net_a.infer_net(img), net_b.infer_net(img)
+    assert (oa["para"] - ob["para"]).abs().max().item() < 3e-2

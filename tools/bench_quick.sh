@@ -1,4 +1,4 @@
-timeout 150 python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err
+timeout 150 python bench.py --steps 10 --warmup 3 --no-cpu ${BENCH_EXTRA} > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err
 python - <<PY
 import json
 d=json.load(open("gpurun_out/bench_quick.json"))

@@ -355,7 +355,8 @@ class Plan(object):
         d = self._conv_desc(op)
         d["flags"] = (1 if x.name in self.f16 else 0) | (2 if y.name in self.f16 else 0)
         if (self.gemm_2x2 and self.conv_algo == "tc" and d["ksize"] == 3 and d["stride"] == 1 and d["pad"] == 1 and
-                d["H"] == 2 and d["W"] == 2 and d["wsets"] == 1 and d["N"] % 8 == 0 and d["N"] >= 32):
+                d["H"] == 2 and d["W"] == 2 and d["wsets"] == 1 and d["N"] % 8 == 0 and d["N"] >= 32 and
+                d["flags"] == 0):
             # the ResNet tail's 2x2-pixel layers as one dense product on the tensor-core path (see
             # conv2x2_as_gemm); the images become an (N/8) x 8 pixel map of a 1x1 convolution
             d2 = dict(N=1, H=d["N"] // 8, W=8, Cin=4 * d["Cin"], Cout=4 * d["Cout"], ksize=1, stride=1, pad=0,

@@ -125,3 +125,57 @@ def test_f16_tensor_selection_rules():
     # nothing is selected on the exact fp32 path
     plan.conv_algo = "simt"
     assert plan._f16_tensors() == set()
+
+
+def test_plan_wires_2x2_convs_as_dense_products():
+    """Host logic of plan.conv2x2_as_gemm: with a test double standing in for the tensor-core kernel, a plan
+    that re-expresses 3x3 convolutions on 2x2-pixel maps as 1x1 convolutions over an (N/8) x 8 pixel map
+    (same buffers, re-laid weights) must reproduce the direct convolution (+ residual + ReLU)."""
+    from danet_b200 import netgraph as ng
+    from danet_b200.plan import Plan
+
+    class FakeTcOps(TorchEmulOps):
+        def __init__(self):
+            self.tc_calls = 0
+
+        def conv_tc_supported(self, d):
+            return d["ksize"] == 1 and d["H"] >= 4 and d["W"] >= 4          # only the transformed layers
+
+        def conv_tc_pack(self, d, w):
+            return w
+
+        def conv2d(self, d, algo, x, w, bias, res, y):
+            if algo == 1:
+                self.tc_calls += 1
+                shp_i, shp_o = (d["N"], d["H"], d["W"], d["Cin"]), (d["N"], d["H"], d["W"], d["Cout"])
+                x, y = x.reshape(shp_i), y.view(shp_o)                         # same memory, other shape
+                res = res.reshape(shp_o) if res is not None else None
+            super().conv2d(d, algo, x, w, bias, res, y)
+
+    g = ng.Graph()
+    C = 16
+    img = g.tensor(1, 2, 2, C, name="image")
+    g.ops.append(dict(op="input", y=img))
+    t1 = g.conv(img, "c1", C, 3, 1, bn="bn1", relu=True)
+    t2 = g.conv(t1, "c2", C, 3, 1, bn="bn2", relu=True, res=img)
+    g.outputs = dict(heads=t2, para=t2)
+    gen = torch.Generator().manual_seed(5)
+    sd = {}
+    for key, spec in g.params.items():
+        if key.endswith("num_batches_tracked"):
+            sd[key] = torch.zeros((), dtype=torch.long)
+        elif key.endswith("running_var"):
+            sd[key] = torch.rand(spec.shape, generator=gen) + 0.5
+        else:
+            sd[key] = torch.randn(spec.shape, generator=gen) * 0.2
+    B = 32
+    x = torch.randn(B, C, 2, 2, generator=gen)
+    outs = []
+    for algo, flag in (("simt", False), ("tc", True)):
+        ops = FakeTcOps()
+        plan = Plan(g, sd, B, "cpu", conv_algo=algo, want_vis=False, ops=ops, gemm_2x2=flag)
+        plan.run(x)
+        outs.append(plan.out("para").clone())
+        assert ops.tc_calls == (2 if flag else 0)
+    assert (outs[0] - outs[1]).abs().max().item() < 1e-5
+    assert outs[0].abs().max().item() > 0.1

@@ -33,6 +33,15 @@ class ConvDesc(ctypes.Structure):
                 ("ksize", c_int), ("stride", c_int), ("pad", c_int), ("wsets", c_int), ("relu", c_int), ("flags", c_int)]
 
 
+class Act(ctypes.Structure):
+    """danet_act: fp32 view and/or split-fp16 planes of one NHWC activation tensor."""
+    _fields_ = [("f32", c_p), ("hi", c_p), ("lo", c_p)]
+
+
+class ConvProblem(ctypes.Structure):
+    _fields_ = [("d", ConvDesc), ("x", Act), ("res", Act), ("y", Act), ("w_packed", c_p), ("bias", c_p)]
+
+
 class GcnParams(ctypes.Structure):
     _fields_ = [("adj", c_p), ("W", c_p * 5), ("b", c_p * 5), ("bn_scale", c_p * 5),
                 ("bn_shift", c_p * 5), ("dim_in", c_int * 5), ("dim_out", c_int * 5),
@@ -61,7 +70,9 @@ SIGNATURES = {
     "danet_conv_tc_packed_bytes": (c_i64, [ctypes.POINTER(ConvDesc)]),
     "danet_conv_tc_pack": (c_int, [ctypes.POINTER(ConvDesc), c_p, c_p, c_p]),
     "danet_conv_tc_supported": (c_int, [ctypes.POINTER(ConvDesc)]),
-    "danet_conv_tc_set_profile_buffer": (c_int, [c_p]),
+    "danet_conv_tc_group": (c_int, [c_int, ctypes.POINTER(ConvProblem), c_p]),
+    "danet_act_split": (c_int, [c_i64, c_p, c_p, c_p, c_p]),
+    "danet_act_merge": (c_int, [c_i64, c_p, c_p, c_p, c_p]),
     "danet_nchw_to_nhwc": (c_int, [c_int, c_int, c_int, c_int, c_p, c_p, c_p]),
     "danet_fuse_sum": (c_int, [c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_int, c_p, c_p]),
     "danet_maxpool3x3s2": (c_int, [c_int, c_int, c_int, c_int, c_p, c_p, c_p]),
@@ -102,9 +113,11 @@ def check(rc, what=""):
         raise RuntimeError("danet_b200 %s failed (rc=%d): %s" % (what, rc, msg.decode() if msg else "?"))
 
 
-def stream_ptr():
+def stream_ptr(device=None):
+    """Current torch stream of `device` (default: the current device).  Callers that own a device pass it
+    and launch under `torch.cuda.device(device)` so that kernels, pointers and stream agree."""
     import torch
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def ptr(t):

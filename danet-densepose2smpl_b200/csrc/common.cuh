@@ -1,6 +1,7 @@
 // Shared helpers for libdanet_b200.so (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -68,5 +69,57 @@ __device__ __forceinline__ uint32_t pack_h2_rn(float lo, float hi) {
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }
+
+// Device view of a danet_act (include/danet_b200.h): fp32 tensor and/or split-fp16 planes of one NHWC activation.
+// Readers prefer the fp32 view when present; writers fill every view that is present.  The split is the one the
+// tensor-core convolution's epilogue applies: hi = rn_f16(v) (saturating), lo = rn_f16(v - hi).
+struct ActV { float* f; __half* hi; __half* lo; };
+static inline ActV actv(const danet_act* a) {
+    ActV v; v.f = a ? a->f32 : nullptr; v.hi = a ? (__half*)a->hi : nullptr; v.lo = a ? (__half*)a->lo : nullptr;
+    return v;
+}
+__device__ __forceinline__ float2 h2_to_f2(uint32_t u) {
+    float2 r;
+    asm("{\n\t.reg .f16 a, b;\n\tmov.b32 {a, b}, %2;\n\tcvt.f32.f16 %0, a;\n\tcvt.f32.f16 %1, b;\n\t}" : "=f"(r.x), "=f"(r.y) : "r"(u));
+    return r;
+}
+// four consecutive channels starting at element e (e % 4 == 0; planes are 8-byte aligned there)
+__device__ __forceinline__ float4 act_ld4(const ActV& a, size_t e) {
+    if (a.f) return __ldg(reinterpret_cast<const float4*>(a.f + e));
+    const uint2 h = __ldg(reinterpret_cast<const uint2*>(a.hi + e));
+    float2 p = h2_to_f2(h.x), q = h2_to_f2(h.y);
+    if (a.lo) {
+        const uint2 l = __ldg(reinterpret_cast<const uint2*>(a.lo + e));
+        const float2 pl = h2_to_f2(l.x), ql = h2_to_f2(l.y);
+        p.x += pl.x; p.y += pl.y; q.x += ql.x; q.y += ql.y;
+    }
+    return make_float4(p.x, p.y, q.x, q.y);
+}
+__device__ __forceinline__ void act_st4(const ActV& a, size_t e, float4 v) {
+    if (a.f) *reinterpret_cast<float4*>(a.f + e) = v;
+    if (a.hi) {
+        const uint32_t h0 = pack_h2_rn(v.x, v.y), h1 = pack_h2_rn(v.z, v.w);
+        *reinterpret_cast<uint2*>(a.hi + e) = make_uint2(h0, h1);
+        if (a.lo) {
+            const float2 p = h2_to_f2(h0), q = h2_to_f2(h1);
+            *reinterpret_cast<uint2*>(a.lo + e) = make_uint2(pack_h2_rn(v.x - p.x, v.y - p.y), pack_h2_rn(v.z - q.x, v.w - q.y));
+        }
+    }
+}
+__device__ __forceinline__ float act_ld1(const ActV& a, size_t e) {
+    if (a.f) return __ldg(a.f + e);
+    float v = __half2float(a.hi[e]);
+    if (a.lo) v += __half2float(a.lo[e]);
+    return v;
+}
+__device__ __forceinline__ void act_st1(const ActV& a, size_t e, float v) {
+    if (a.f) a.f[e] = v;
+    if (a.hi) {
+        const __half h = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+        a.hi[e] = h;
+        if (a.lo) a.lo[e] = __float2half_rn(v - __half2float(h));
+    }
+}
+static inline bool act_any(const danet_act* a) { return a && (a->f32 || a->hi); }
 
 }  // namespace danet

@@ -161,9 +161,6 @@ int conv_simt_launch(const danet_conv_desc* d, const float* x, const float* w, c
     return 0;
 }
 
-int conv_tc_launch(const danet_conv_desc* d, const void* x, const void* w_packed, const float* bias,
-                   const float* residual, void* y, cudaStream_t stream);   // conv_tc.cu
-
 }  // namespace danet
 
 using namespace danet;
@@ -184,14 +181,7 @@ extern "C" int danet_conv2d(const danet_conv_desc* d, int32_t algo, const void* 
     if (check_conv_desc(d) != 0) return -1;
     if (d->N == 0) return 0;
     DANET_CHECK(x && w && y, "danet_conv2d: null pointer");
-    DANET_CHECK((d->flags & ~(DANET_CONV_X_F16 | DANET_CONV_Y_F16)) == 0, "danet_conv2d: unknown flags 0x%x", d->flags);
-    if (algo == DANET_CONV_SIMT) {
-        DANET_CHECK(d->flags == 0, "danet_conv2d: fp16 tensors are only taken by the tensor-core path");
-        return conv_simt_launch(d, (const float*)x, w, bias, residual, (float*)y, (cudaStream_t)stream);
-    }
-    if (algo == DANET_CONV_TC) {
-        DANET_CHECK(danet_conv_tc_supported(d), "danet_conv2d: shape not supported by the tcgen05 path");
-        return conv_tc_launch(d, x, (const void*)w, bias, residual, y, (cudaStream_t)stream);
-    }
-    DANET_CHECK(false, "danet_conv2d: unknown algo %d", algo);
+    DANET_CHECK(algo == DANET_CONV_SIMT, "danet_conv2d: algo %d -- the tensor-core path is danet_conv_tc_group (split-fp16 activations)", algo);
+    DANET_CHECK(d->flags == 0, "danet_conv2d: flags are only taken by the tensor-core path");
+    return conv_simt_launch(d, (const float*)x, w, bias, residual, (float*)y, (cudaStream_t)stream);
 }

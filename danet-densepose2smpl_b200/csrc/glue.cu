@@ -34,18 +34,18 @@ __device__ __forceinline__ int argmax_first(const float* v, int n) {
 // ------------------------------------------------------------------------------------------
 // NCHW image -> NHWC padded (input boundary of the network; demo.py:106 / eval.py:147 tensors)
 // ------------------------------------------------------------------------------------------
-__global__ void k_nchw_to_nhwc(int N, int C, int HW, int Cp, const float* __restrict__ x, float* __restrict__ y) {
+__global__ void k_nchw_to_nhwc(int N, int C, int HW, int Cp, const float* __restrict__ x, ActV y) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)N * HW) return;
     const int n = (int)(i / HW), p = (int)(i % HW);
-    for (int c = 0; c < Cp; ++c) y[i * Cp + c] = c < C ? x[((size_t)n * C + c) * HW + p] : 0.0f;
+    for (int c = 0; c < Cp; ++c) act_st1(y, i * Cp + c, c < C ? x[((size_t)n * C + c) * HW + p] : 0.0f);
 }
 
 // ------------------------------------------------------------------------------------------
 // iuvmap_clean, global heads (utils/iuvmap.py:6-38 via danet.py:79 / iuv_estimator.py:127)
 // ------------------------------------------------------------------------------------------
 __global__ void k_iuv_clean_global(int B, int HW, int Chead, int off_u, int off_v, int off_i, int off_a,
-                                   int Cb, const float* __restrict__ heads, float* __restrict__ body,
+                                   int Cb, const float* __restrict__ heads, ActV body,
                                    uint8_t* __restrict__ amax, float* un, float* vn, float* in_, float* an) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * HW) return;
@@ -56,16 +56,16 @@ __global__ void k_iuv_clean_global(int B, int HW, int Chead, int off_u, int off_
     for (int c = 0; c < 25; ++c) I[c] = h[off_i + c];
     const int best = argmax_first(I, 25);
     amax[i] = (uint8_t)best;
-    float* o = body + (size_t)i * Cb;
+    const size_t o = (size_t)i * Cb;
     for (int c = 0; c < 25; ++c) {
         const float oh = (c == best) ? 1.0f : 0.0f;
         const float u = oh * h[off_u + c], v = oh * h[off_v + c];
-        o[c] = u; o[25 + c] = v; o[50 + c] = oh;
+        act_st1(body, o + c, u); act_st1(body, o + 25 + c, v); act_st1(body, o + 50 + c, oh);
         if (un) un[((size_t)b * 25 + c) * HW + pix] = u;
         if (vn) vn[((size_t)b * 25 + c) * HW + pix] = v;
         if (in_) in_[((size_t)b * 25 + c) * HW + pix] = oh;
     }
-    for (int c = 75; c < Cb; ++c) o[c] = 0.0f;
+    for (int c = 75; c < Cb; ++c) act_st1(body, o + c, 0.0f);
     if (an) {
 #pragma unroll
         for (int c = 0; c < 15; ++c) A[c] = h[off_a + c];
@@ -78,7 +78,7 @@ __global__ void k_iuv_clean_global(int B, int HW, int Chead, int off_u, int off_
 // written as 16-byte vectors when Cx, Cy are multiples of 4 -- they are, the graph pads channels)
 template <bool VEC>
 __global__ void k_iuv_clean_parts(int N, int HW, int Cx, int Cy, const float* __restrict__ x,
-                                  void* __restrict__ yv, float* raw, int y_f16) {
+                                  ActV y, float* raw) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)N * HW) return;
     const float* h = x + i * Cx;
@@ -94,7 +94,6 @@ __global__ void k_iuv_clean_parts(int N, int HW, int Cx, int Cy, const float* __
         for (int c = 0; c < 21; ++c) v[c] = h[c];
     }
     const int best = argmax_first(v + 14, 7);
-    float* o = reinterpret_cast<float*>(yv) + i * Cy;                 // fp32 view (unused when y_f16)
     float ov[24];
 #pragma unroll
     for (int c = 0; c < 7; ++c) {
@@ -102,22 +101,14 @@ __global__ void k_iuv_clean_parts(int N, int HW, int Cx, int Cy, const float* __
         ov[c] = oh * v[c]; ov[7 + c] = oh * v[7 + c]; ov[14 + c] = oh;
     }
     ov[21] = ov[22] = ov[23] = 0.0f;
-    if (VEC && y_f16) {
-        uint4* oh = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(yv) + i * Cy);     // Cy % 8 == 0
+    if (VEC) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
-            oh[c] = make_uint4(pack_h2_rn(ov[8 * c], ov[8 * c + 1]), pack_h2_rn(ov[8 * c + 2], ov[8 * c + 3]),
-                               pack_h2_rn(ov[8 * c + 4], ov[8 * c + 5]), pack_h2_rn(ov[8 * c + 6], ov[8 * c + 7]));
-        for (int c = 3; c < Cy / 8; ++c) oh[c] = make_uint4(0u, 0u, 0u, 0u);
-    } else if (VEC) {
-#pragma unroll
-        for (int c = 0; c < 6; ++c)
-            reinterpret_cast<float4*>(o)[c] = make_float4(ov[4 * c], ov[4 * c + 1], ov[4 * c + 2], ov[4 * c + 3]);
-        for (int c = 24; c < Cy; ++c) o[c] = 0.0f;
+        for (int c = 0; c < 6; ++c) act_st4(y, i * Cy + 4 * c, make_float4(ov[4 * c], ov[4 * c + 1], ov[4 * c + 2], ov[4 * c + 3]));
+        for (int c = 24; c < Cy; ++c) act_st1(y, i * Cy + c, 0.0f);
     } else {
 #pragma unroll
-        for (int c = 0; c < 21; ++c) o[c] = ov[c];
-        for (int c = 21; c < Cy; ++c) o[c] = 0.0f;
+        for (int c = 0; c < 21; ++c) act_st1(y, i * Cy + c, ov[c]);
+        for (int c = 21; c < Cy; ++c) act_st1(y, i * Cy + c, 0.0f);
     }
     if (raw) {
         const size_t n = i / HW, pix = i - n * HW;
@@ -249,8 +240,8 @@ k_stn_params(int B, int S, int Chm, const float* __restrict__ hm, const uint8_t*
 // grid = one block per (crop b*24+part, output row py); threads run over (px, 4-channel group) of the row: the
 // per-element 64-bit div/mod chain of the first version cost more than the 16-byte store it fed
 __global__ void __launch_bounds__(256)
-k_stn_sample(int B, int S, int C, const float* __restrict__ xd, const float* __restrict__ theta,
-             int align_corners, void* __restrict__ crops, int out_f16) {
+k_stn_sample(int B, int S, int C, ActV xd, const float* __restrict__ theta,
+             int align_corners, ActV crops) {
     const int C4 = C >> 2;
     const int bp = blockIdx.x / S, py = blockIdx.x - bp * S;
     const int b = bp / 24;
@@ -267,7 +258,7 @@ k_stn_sample(int B, int S, int C, const float* __restrict__ xd, const float* __r
     const float ty = iy - fy;
     const bool y_ok = fy > -2.0f && fy < (float)S + 1.0f;
     const int y0 = y_ok ? (int)fy : 0;
-    const float* img = xd + (size_t)b * S * S * C;
+    const size_t ibase = (size_t)b * S * S * C;
     const size_t obase = ((size_t)bp * S + py) * S * C4;            // in 4-channel groups
     const int items = S * C4;
     for (int i = threadIdx.x; i < items; i += blockDim.x) {
@@ -285,7 +276,6 @@ k_stn_sample(int B, int S, int C, const float* __restrict__ xd, const float* __r
         // guard against huge coordinates before the int conversion
         if (y_ok && fx > -2.0f && fx < (float)S + 1.0f) {
             const int x0 = (int)fx;
-            const float* base = img + c4 * 4;
 #pragma unroll
             for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
@@ -293,24 +283,23 @@ k_stn_sample(int B, int S, int C, const float* __restrict__ xd, const float* __r
                     const int xx = x0 + dx, yy = y0 + dy;
                     if (xx < 0 || xx >= S || yy < 0 || yy >= S) continue;
                     const float w = (dx ? tx : 1.0f - tx) * (dy ? ty : 1.0f - ty);
-                    const float4 v = __ldg(reinterpret_cast<const float4*>(base + (size_t)(yy * S + xx) * C));
+                    const float4 v = act_ld4(xd, ibase + (size_t)(yy * S + xx) * C + c4 * 4);
                     acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
                     acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
                 }
         }
-        if (out_f16) reinterpret_cast<uint2*>(crops)[obase + i] = make_uint2(pack_h2_rn(acc.x, acc.y), pack_h2_rn(acc.z, acc.w));
-        else reinterpret_cast<float4*>(crops)[obase + i] = acc;
+        act_st4(crops, (obase + i) * 4, acc);
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // HRNet fuse (hr_module.py:161-179): y = relu(sum_j nearest_up(t_j))
 // ------------------------------------------------------------------------------------------
-struct FuseArgs { const float* t[4]; int f[4]; int n; };      // f = log2 of the upsample factor (1,2,4,8 -> 0..3)
+struct FuseArgs { ActV t[4]; int f[4]; int n; };      // f = log2 of the upsample factor (1,2,4,8 -> 0..3)
 
 // grid = (n*H + h, chunks of a row): no per-element 64-bit division
 __global__ void __launch_bounds__(256)
-k_fuse_sum(int N, int H, int W, int C4, unsigned long long mC4, FuseArgs a, int relu, float* __restrict__ y) {
+k_fuse_sum(int N, int H, int W, int C4, unsigned long long mC4, FuseArgs a, int relu, ActV y) {
     const int row = blockIdx.x;
     const int n = row / H, h = row - n * H;
     const int i = blockIdx.y * blockDim.x + threadIdx.x;
@@ -321,17 +310,16 @@ k_fuse_sum(int N, int H, int W, int C4, unsigned long long mC4, FuseArgs a, int 
     for (int j = 0; j < 4; ++j) {
         if (j >= a.n) break;
         const int sh = a.f[j];
-        const float4 v = __ldg(reinterpret_cast<const float4*>(a.t[j]) +
-                               ((size_t)(n * (H >> sh) + (h >> sh)) * (W >> sh) + (w >> sh)) * C4 + c4);
+        const float4 v = act_ld4(a.t[j], (((size_t)(n * (H >> sh) + (h >> sh)) * (W >> sh) + (w >> sh)) * C4 + c4) * 4);
         if (j == 0) acc = v;
         else { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
     }
     if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
-    reinterpret_cast<float4*>(y)[(size_t)row * W * C4 + i] = acc;
+    act_st4(y, ((size_t)row * W * C4 + i) * 4, acc);
 }
 
 __global__ void __launch_bounds__(256)
-k_maxpool3x3s2(int N, int H, int W, int C4, const float* __restrict__ x, float* __restrict__ y) {
+k_maxpool3x3s2(int N, int H, int W, int C4, ActV x, ActV y) {
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
     const int row = blockIdx.x;
     const int n = row / Ho, ho = row - n * Ho;
@@ -345,19 +333,19 @@ k_maxpool3x3s2(int N, int H, int W, int C4, const float* __restrict__ x, float* 
         for (int dx = 0; dx < 3; ++dx) {
             const int ww = wo * 2 - 1 + dx;
             if (ww < 0 || ww >= W) continue;
-            const float4 v = __ldg(reinterpret_cast<const float4*>(x) + ((size_t)(n * H + hh) * W + ww) * C4 + c4);
+            const float4 v = act_ld4(x, (((size_t)(n * H + hh) * W + ww) * C4 + c4) * 4);
             m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
         }
     }
-    reinterpret_cast<float4*>(y)[(size_t)row * Wo * C4 + i] = m;
+    act_st4(y, ((size_t)row * Wo * C4 + i) * 4, m);
 }
 
-__global__ void k_global_avgpool(int N, int HW, int C, const float* __restrict__ x, float* __restrict__ y) {
+__global__ void k_global_avgpool(int N, int HW, int C, ActV x, float* __restrict__ y) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N * C) return;
     const int n = i / C, c = i % C;
     float s = 0.f;
-    for (int p = 0; p < HW; ++p) s += x[((size_t)n * HW + p) * C + c];
+    for (int p = 0; p < HW; ++p) s += act_ld1(x, ((size_t)n * HW + p) * C + c);
     y[i] = s / (float)HW;
 }
 
@@ -477,42 +465,54 @@ k_gcn_pose_head(int B, GcnArgs g, const float* __restrict__ rot_feats, const flo
 
 using namespace danet;
 
-extern "C" int danet_nchw_to_nhwc(int32_t N, int32_t C, int32_t HW, int32_t Cp, const float* x, float* y,
+static int check_act(const danet_act* a, const char* what, bool need_c8 = false, int C = 8) {
+    DANET_CHECK(act_any(a), "%s: activation has neither an fp32 view nor fp16 planes", what);
+    DANET_CHECK(!(a->lo && !a->hi), "%s: lo plane without hi plane", what);
+    DANET_CHECK(!a->hi || C % 4 == 0, "%s: fp16 planes need C %% 4 == 0 (got %d)", what, C);
+    (void)need_c8;
+    return 0;
+}
+
+extern "C" int danet_nchw_to_nhwc(int32_t N, int32_t C, int32_t HW, int32_t Cp, const float* x, const danet_act* y,
                                   danet_stream_t s) {
     DANET_CHECK(N >= 0 && C > 0 && Cp >= C && HW > 0, "danet_nchw_to_nhwc: bad sizes");
     if (N == 0) return 0;
-    DANET_CHECK(x && y, "danet_nchw_to_nhwc: null pointer");
-    k_nchw_to_nhwc<<<cdiv(N * HW, 256), 256, 0, (cudaStream_t)s>>>(N, C, HW, Cp, x, y);
+    DANET_CHECK(x, "danet_nchw_to_nhwc: null pointer");
+    if (check_act(y, "danet_nchw_to_nhwc", false, 4) != 0) return -1;
+    k_nchw_to_nhwc<<<cdiv(N * HW, 256), 256, 0, (cudaStream_t)s>>>(N, C, HW, Cp, x, actv(y));
     DANET_LAUNCH_CHECK();
     return 0;
 }
 
 extern "C" int danet_iuv_clean_global(int32_t B, int32_t HW, int32_t Chead, int32_t off_u, int32_t off_v,
                                       int32_t off_i, int32_t off_a, int32_t Cbody, const float* heads,
-                                      float* body_iuv, uint8_t* index_argmax, float* u_nchw, float* v_nchw,
+                                      const danet_act* body_iuv, uint8_t* index_argmax, float* u_nchw, float* v_nchw,
                                       float* i_nchw, float* ann_nchw, danet_stream_t s) {
     DANET_CHECK(B >= 0 && HW > 0 && Cbody >= 75, "danet_iuv_clean_global: bad sizes");
     DANET_CHECK(off_u + 25 <= Chead && off_v + 25 <= Chead && off_i + 25 <= Chead && off_a + 15 <= Chead,
                 "danet_iuv_clean_global: head offsets exceed Chead=%d", Chead);
     if (B == 0) return 0;
-    DANET_CHECK(heads && body_iuv && index_argmax, "danet_iuv_clean_global: null pointer");
+    DANET_CHECK(heads && index_argmax, "danet_iuv_clean_global: null pointer");
+    if (check_act(body_iuv, "danet_iuv_clean_global", false, 4) != 0) return -1;
     k_iuv_clean_global<<<cdiv(B * HW, 128), 128, 0, (cudaStream_t)s>>>(B, HW, Chead, off_u, off_v, off_i, off_a, Cbody,
-                                                                     heads, body_iuv, index_argmax, u_nchw, v_nchw,
+                                                                     heads, actv(body_iuv), index_argmax, u_nchw, v_nchw,
                                                                      i_nchw, ann_nchw);
     DANET_LAUNCH_CHECK();
     return 0;
 }
 
-extern "C" int danet_iuv_clean_parts(int32_t N, int32_t HW, int32_t Cx, int32_t Cy, const float* x, void* y,
-                                     float* raw_nchw, int32_t y_f16, danet_stream_t s) {
+extern "C" int danet_iuv_clean_parts(int32_t N, int32_t HW, int32_t Cx, int32_t Cy, const float* x, const danet_act* y,
+                                     float* raw_nchw, danet_stream_t s) {
     DANET_CHECK(N >= 0 && HW > 0 && Cx >= 21 && Cy >= 21, "danet_iuv_clean_parts: bad sizes");
     if (N == 0) return 0;
-    DANET_CHECK(x && y, "danet_iuv_clean_parts: null pointer");
-    DANET_CHECK(!y_f16 || (Cx % 4 == 0 && Cx >= 24 && Cy % 8 == 0 && Cy >= 24), "danet_iuv_clean_parts: fp16 output needs Cx %% 4 == 0, Cy %% 8 == 0");
+    DANET_CHECK(x, "danet_iuv_clean_parts: null pointer");
+    if (check_act(y, "danet_iuv_clean_parts", false, Cy) != 0) return -1;
     if (Cx % 4 == 0 && Cy % 4 == 0 && Cx >= 24 && Cy >= 24)
-        k_iuv_clean_parts<true><<<cdiv((int64_t)N * HW, 128), 128, 0, (cudaStream_t)s>>>(N, HW, Cx, Cy, x, y, raw_nchw, y_f16);
-    else
-        k_iuv_clean_parts<false><<<cdiv((int64_t)N * HW, 128), 128, 0, (cudaStream_t)s>>>(N, HW, Cx, Cy, x, y, raw_nchw, 0);
+        k_iuv_clean_parts<true><<<cdiv((int64_t)N * HW, 128), 128, 0, (cudaStream_t)s>>>(N, HW, Cx, Cy, x, actv(y), raw_nchw);
+    else {
+        DANET_CHECK(!y->hi, "danet_iuv_clean_parts: fp16 planes need Cx, Cy >= 24 and %% 4 == 0");
+        k_iuv_clean_parts<false><<<cdiv((int64_t)N * HW, 128), 128, 0, (cudaStream_t)s>>>(N, HW, Cx, Cy, x, actv(y), raw_nchw);
+    }
     DANET_LAUNCH_CHECK();
     return 0;
 }
@@ -529,54 +529,58 @@ extern "C" int danet_stn_params(int32_t B, int32_t S, int32_t Chm, const float* 
     return 0;
 }
 
-extern "C" int danet_stn_sample(int32_t B, int32_t S, int32_t C, const float* xd, const float* theta,
-                                int32_t align_corners, void* crops, int32_t out_f16, danet_stream_t s) {
+extern "C" int danet_stn_sample(int32_t B, int32_t S, int32_t C, const danet_act* xd, const float* theta,
+                                int32_t align_corners, const danet_act* crops, danet_stream_t s) {
     DANET_CHECK(B >= 0 && S > 1 && C > 0 && C % 4 == 0, "danet_stn_sample: bad sizes (C %% 4 must be 0)");
     if (B == 0) return 0;
-    DANET_CHECK(xd && theta && crops, "danet_stn_sample: null pointer");
+    DANET_CHECK(theta, "danet_stn_sample: null pointer");
+    if (check_act(xd, "danet_stn_sample(xd)", false, C) != 0 || check_act(crops, "danet_stn_sample(crops)", false, C) != 0) return -1;
     DANET_CHECK((int64_t)B * 24 * S < (1LL << 31), "danet_stn_sample: batch too large for one launch");
     const int items = S * (C / 4);
-    k_stn_sample<<<B * 24 * S, items >= 256 ? 256 : (items + 31) / 32 * 32, 0, (cudaStream_t)s>>>(B, S, C, xd, theta, align_corners, crops, out_f16);
+    k_stn_sample<<<B * 24 * S, items >= 256 ? 256 : (items + 31) / 32 * 32, 0, (cudaStream_t)s>>>(B, S, C, actv(xd), theta, align_corners, actv(crops));
     DANET_LAUNCH_CHECK();
     return 0;
 }
 
-extern "C" int danet_fuse_sum(int32_t N, int32_t H, int32_t W, int32_t C, int32_t nterms, const float* const* terms,
-                              const int32_t* factors, int32_t relu, float* y, danet_stream_t s) {
+extern "C" int danet_fuse_sum(int32_t N, int32_t H, int32_t W, int32_t C, int32_t nterms, const danet_act* terms,
+                              const int32_t* factors, int32_t relu, const danet_act* y, danet_stream_t s) {
     DANET_CHECK(N >= 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "danet_fuse_sum: bad sizes (C %% 4 must be 0)");
-    DANET_CHECK(nterms >= 1 && nterms <= 4 && terms && factors && y, "danet_fuse_sum: 1..4 terms required");
+    DANET_CHECK(nterms >= 1 && nterms <= 4 && terms && factors, "danet_fuse_sum: 1..4 terms required");
     if (N == 0) return 0;
+    if (check_act(y, "danet_fuse_sum(y)", false, C) != 0) return -1;
     FuseArgs a;
     a.n = nterms;
-    for (int j = 0; j < 4; ++j) { a.t[j] = nullptr; a.f[j] = 1; }
+    for (int j = 0; j < 4; ++j) { a.t[j] = actv(nullptr); a.f[j] = 1; }
     for (int j = 0; j < nterms; ++j) {
         const int f = factors[j];
-        DANET_CHECK(terms[j] && (f == 1 || f == 2 || f == 4 || f == 8) && H % f == 0 && W % f == 0,
+        DANET_CHECK((f == 1 || f == 2 || f == 4 || f == 8) && H % f == 0 && W % f == 0,
                     "danet_fuse_sum: term %d has bad upsample factor %d for %dx%d", j, f, H, W);
-        a.t[j] = terms[j]; a.f[j] = f == 1 ? 0 : (f == 2 ? 1 : (f == 4 ? 2 : 3));
+        if (check_act(&terms[j], "danet_fuse_sum(term)", false, C) != 0) return -1;
+        a.t[j] = actv(&terms[j]); a.f[j] = f == 1 ? 0 : (f == 2 ? 1 : (f == 4 ? 2 : 3));
     }
     DANET_CHECK((int64_t)N * H < (1LL << 31) && (int64_t)W * (C / 4) < (1 << 24) && C / 4 < (1 << 16), "danet_fuse_sum: tensor too large for one launch");
-    k_fuse_sum<<<dim3(N * H, cdiv(W * (C / 4), 256)), 256, 0, (cudaStream_t)s>>>(N, H, W, C / 4, (1ull << 40) / (unsigned long long)(C / 4) + 1ull, a, relu, y);
+    k_fuse_sum<<<dim3(N * H, cdiv(W * (C / 4), 256)), 256, 0, (cudaStream_t)s>>>(N, H, W, C / 4, (1ull << 40) / (unsigned long long)(C / 4) + 1ull, a, relu, actv(y));
     DANET_LAUNCH_CHECK();
     return 0;
 }
 
-extern "C" int danet_maxpool3x3s2(int32_t N, int32_t H, int32_t W, int32_t C, const float* x, float* y, danet_stream_t s) {
+extern "C" int danet_maxpool3x3s2(int32_t N, int32_t H, int32_t W, int32_t C, const danet_act* x, const danet_act* y, danet_stream_t s) {
     DANET_CHECK(N >= 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "danet_maxpool3x3s2: bad sizes (C %% 4 must be 0)");
     if (N == 0) return 0;
-    DANET_CHECK(x && y, "danet_maxpool3x3s2: null pointer");
+    if (check_act(x, "danet_maxpool3x3s2(x)", false, C) != 0 || check_act(y, "danet_maxpool3x3s2(y)", false, C) != 0) return -1;
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
     DANET_CHECK((int64_t)N * Ho < (1LL << 31) && (int64_t)Wo * (C / 4) <= 65535LL * 256, "danet_maxpool3x3s2: tensor too large for one launch");
-    k_maxpool3x3s2<<<dim3(N * Ho, cdiv(Wo * (C / 4), 256)), 256, 0, (cudaStream_t)s>>>(N, H, W, C / 4, x, y);
+    k_maxpool3x3s2<<<dim3(N * Ho, cdiv(Wo * (C / 4), 256)), 256, 0, (cudaStream_t)s>>>(N, H, W, C / 4, actv(x), actv(y));
     DANET_LAUNCH_CHECK();
     return 0;
 }
 
-extern "C" int danet_global_avgpool(int32_t N, int32_t HW, int32_t C, const float* x, float* y, danet_stream_t s) {
+extern "C" int danet_global_avgpool(int32_t N, int32_t HW, int32_t C, const danet_act* x, float* y, danet_stream_t s) {
     DANET_CHECK(N >= 0 && HW > 0 && C > 0, "danet_global_avgpool: bad sizes");
     if (N == 0) return 0;
-    DANET_CHECK(x && y, "danet_global_avgpool: null pointer");
-    k_global_avgpool<<<cdiv(N * C, 256), 256, 0, (cudaStream_t)s>>>(N, HW, C, x, y);
+    DANET_CHECK(y, "danet_global_avgpool: null pointer");
+    if (check_act(x, "danet_global_avgpool", false, 4) != 0) return -1;
+    k_global_avgpool<<<cdiv(N * C, 256), 256, 0, (cudaStream_t)s>>>(N, HW, C, actv(x), y);
     DANET_LAUNCH_CHECK();
     return 0;
 }

@@ -116,10 +116,12 @@ int danet_iuv_img2map(int32_t B, int32_t S, const float* img, float* maps_u, flo
                       float* maps_i, float* maps_ann, danet_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
- * Network half (models/danet/*, models/module/*).  fp32 NHWC activations.
+ * Network half (models/danet/*, models/module/*).  NHWC activations as danet_act views (fp32 and/or
+ * split-fp16 planes): every glue kernel below reads the fp32 view when present, else hi(+lo), and writes
+ * every view that is present.
  * ------------------------------------------------------------------------------------------ */
-enum { DANET_CONV_SIMT = 0,            /* fp32 FMA implicit GEMM (exact-parity path)               */
-       DANET_CONV_TC = 1 };            /* tcgen05 TF32 tensor-core implicit GEMM (fast path)       */
+enum { DANET_CONV_SIMT = 0,            /* fp32 FMA implicit GEMM (independent fp32 check path)      */
+       DANET_CONV_TC = 1 };            /* tcgen05 tensor-core implicit GEMM (danet_conv_tc_group)   */
 
 typedef struct {
     int32_t N, H, W, Cin;              /* input  [N,H,W,Cin]                                      */
@@ -128,45 +130,62 @@ typedef struct {
                                           res_module.py:335-342,500-535 become wsets=24 over the
                                           (batch,part)-flattened image axis)                       */
     int32_t relu;                      /* apply ReLU last                                         */
-    int32_t flags;                     /* tensor-core path only: DANET_CONV_X_F16 / DANET_CONV_Y_F16 --
-                                          x / y are IEEE fp16 NHWC buffers (Cin resp. Cout % 8 == 0).
-                                          The tcgen05 kernel rounds its activations to fp16 (RN) anyway;
-                                          storing an intermediate that only feeds such convolutions in
-                                          fp16 moves that rounding into the producer's epilogue: same
-                                          bits, half the traffic.  residual / bias stay fp32.            */
+    int32_t flags;                     /* tensor-core path: DANET_CONV_EXACT                      */
 } danet_conv_desc;
-#define DANET_CONV_X_F16 1
-#define DANET_CONV_Y_F16 2
+/* tensor-core path, exact mode: three MMAs per K step on split-fp16 operands (hi*hi + hi*lo + lo*hi,
+ * fp32 accumulation): fp32-grade results (the reference computes these layers in fp32).  Without the flag
+ * only hi*hi is issued (fp16-operand precision, ~1e-3 on the network output). */
+#define DANET_CONV_EXACT 4
+
+/* An activation tensor of the network half, NHWC.  Any subset of the three views may be present:
+ *   f32      fp32 [N,H,W,C]
+ *   hi / lo  SPLIT-FP16 planes, each IEEE fp16 [N,H,W,C], C % 8 == 0, 16-byte aligned:
+ *            value = float(hi) + float(lo), hi = rn(value), lo = rn(value - hi)  (22 significant bits);
+ *            lo == NULL means "hi only" (fast mode).
+ * Tensor-core convolutions read hi/lo through TMA tensor maps and write any of the views. */
+typedef struct { float* f32; void* hi; void* lo; } danet_act;
 
 /* Weight packing for the SIMT path: w [wsets][ksize*ksize*Cin][Cout] (tap-major, then cin),
  * bias [wsets][Cout] (BN folded by the caller).  residual (or NULL) has the output's shape and is
- * added before the ReLU (res_module.py:40-56,77-97). */
+ * added before the ReLU (res_module.py:40-56,77-97).  fp32 tensors only. */
 int danet_conv2d(const danet_conv_desc* d, int32_t algo, const void* x, const float* w,
                  const float* bias, const float* residual, void* y, danet_stream_t stream);
-/* bytes / packing helper for the tensor-core path: converts the SIMT layout above into the
- * shared-memory image blocks the tcgen05 kernel bulk-copies (device -> device, once at load). */
+
+/* Tensor-core path.  One launch runs up to 6 independent convolutions (e.g. the parallel branches of an
+ * HRNet stage, hr_module.py:165-166) over one persistent grid.  w_packed comes from danet_conv_tc_pack with
+ * the SAME descriptor (flags included).  x needs hi (+ lo in exact mode); res: f32, or hi(+lo), or all NULL;
+ * y: f32 and/or hi(+lo).  Cin % 8 == 0, Cout % 8 == 0 (pad channels carry zero weights / zero data). */
+typedef struct {
+    danet_conv_desc d;
+    danet_act x, res, y;
+    const void* w_packed;
+    const float* bias;                 /* [wsets][Cout] or NULL */
+} danet_conv_problem;
+int danet_conv_tc_group(int32_t n, const danet_conv_problem* problems, danet_stream_t stream);
+/* bytes / packing helper: converts the SIMT layout above into the swizzled shared-memory image blocks of
+ * split-fp16 weights the tcgen05 kernel bulk-copies (device -> device, once at load). */
 int64_t danet_conv_tc_packed_bytes(const danet_conv_desc* d);
 int danet_conv_tc_pack(const danet_conv_desc* d, const float* w_simt, void* w_packed, danet_stream_t stream);
 int danet_conv_tc_supported(const danet_conv_desc* d);
-/* bring-up instrumentation: 16 x int64 device buffer receiving per-role cycle counters of CTA 0 of
- * every following tensor-core launch (NULL = off) */
-int danet_conv_tc_set_profile_buffer(void* dev_buf);
+/* fp32 -> split-fp16 planes (lo may be NULL) and back (lo may be NULL); n elements */
+int danet_act_split(int64_t n, const float* x, void* hi, void* lo, danet_stream_t stream);
+int danet_act_merge(int64_t n, const void* hi, const void* lo, float* y, danet_stream_t stream);
 
 /* input boundary: x NCHW [N,C,HW] -> y NHWC [N,HW,Cp] with Cp >= C zero-padded channels
  * (images arrive NCHW: demo.py:106, eval.py:147) */
-int danet_nchw_to_nhwc(int32_t N, int32_t C, int32_t HW, int32_t Cp, const float* x, float* y,
+int danet_nchw_to_nhwc(int32_t N, int32_t C, int32_t HW, int32_t Cp, const float* x, const danet_act* y,
                        danet_stream_t stream);
 
 /* hr_module.py:161-179 fuse: y = relu(sum_j up_{f_j}(t_j)); t_j [N,H/f_j,W/f_j,C] nearest-upsampled
  * by f_j in {1,2,4,8}; nterms <= 4; summed in argument order */
 int danet_fuse_sum(int32_t N, int32_t H, int32_t W, int32_t C, int32_t nterms,
-                   const float* const* terms, const int32_t* factors, int32_t relu, float* y,
+                   const danet_act* terms /*[nterms]*/, const int32_t* factors, int32_t relu, const danet_act* y,
                    danet_stream_t stream);
 /* nn.MaxPool2d(3,2,1) (res_module.py:409) NHWC */
-int danet_maxpool3x3s2(int32_t N, int32_t H, int32_t W, int32_t C, const float* x, float* y,
+int danet_maxpool3x3s2(int32_t N, int32_t H, int32_t W, int32_t C, const danet_act* x, const danet_act* y,
                        danet_stream_t stream);
 /* nn.AdaptiveAvgPool2d(1) NHWC [N,H,W,C] -> [N,C] */
-int danet_global_avgpool(int32_t N, int32_t HW, int32_t C, const float* x, float* y, danet_stream_t stream);
+int danet_global_avgpool(int32_t N, int32_t HW, int32_t C, const danet_act* x, float* y, danet_stream_t stream);
 /* y[n,o] = sum_i x[n,i] w[o,i] + b[o] (+ add[o])  (SmplResNet.final_layer + mean_cam_shape) */
 int danet_linear(int32_t N, int32_t In, int32_t Out, const float* x, const float* w, const float* b,
                  const float* add, float* y, danet_stream_t stream);
@@ -178,7 +197,7 @@ int danet_linear(int32_t N, int32_t In, int32_t Out, const float* x, const float
  * uint8 argmax map [B,HW]; optional NCHW outputs u/v/i [B,25,HW], ann [B,15,HW] (danet.py:81). */
 int danet_iuv_clean_global(int32_t B, int32_t HW, int32_t Chead, int32_t off_u, int32_t off_v,
                            int32_t off_i, int32_t off_a, int32_t Cbody, const float* heads,
-                           float* body_iuv, uint8_t* index_argmax, float* u_nchw, float* v_nchw,
+                           const danet_act* body_iuv, uint8_t* index_argmax, float* u_nchw, float* v_nchw,
                            float* i_nchw, float* ann_nchw, danet_stream_t stream);
 /* utils/iuvmap.py:6-38 with the reference's own signature: NCHW maps U,V,Index [B,C,HW] and
  * optional AnnIndex [B,Ca,HW] (NULL to skip) -> cleaned maps of the same shapes */
@@ -189,10 +208,8 @@ int danet_iuvmap_clean_nchw(int32_t B, int32_t C, int32_t Ca, int32_t HW, const 
  * first 21 channels (N = batch*24) -> y [N,HW,Cy>=21] cleaned (pad channels zeroed); optional raw
  * copy in the reference's
  * layout part_iuv_pred [N,21,HW] (iuv_estimator.py:208-211). */
-/* y_f16 != 0: y is an fp16 [N,HW,Cy] buffer (Cy % 8 == 0) for a tensor-core convolution, same RN
- * rounding that convolution would apply to the fp32 values (see danet_conv_desc.flags). */
-int danet_iuv_clean_parts(int32_t N, int32_t HW, int32_t Cx, int32_t Cy, const float* x, void* y,
-                          float* raw_nchw, int32_t y_f16, danet_stream_t stream);
+int danet_iuv_clean_parts(int32_t N, int32_t HW, int32_t Cx, int32_t Cy, const float* x, const danet_act* y,
+                          float* raw_nchw, danet_stream_t stream);
 /* iuv_estimator.py:137-140,176-184,262-301: soft-argmax centres of 10*hm, part visibility,
  * affine thetas.  hm [B,HW,Chm] (24 heatmap channels first), index_argmax [B,HW] ->
  * centers [B,24,2] (x,y in [-1,1]), theta [B,24,3] = (scale, cx, cy).
@@ -203,9 +220,8 @@ int danet_stn_params(int32_t B, int32_t S, int32_t Chm, const float* hm, const u
                      int32_t align_corners, float* centers, float* theta, danet_stream_t stream);
 /* iuv_estimator.py:193-204: 24x affine_grid + grid_sample (bilinear, zeros) of xd [B,S,S,C]
  * -> crops [B*24,S,S,C] (image index b*24+part) */
-/* out_f16 != 0: crops is an fp16 buffer (consumed only by the grouped tensor-core convolution). */
-int danet_stn_sample(int32_t B, int32_t S, int32_t C, const float* xd, const float* theta,
-                     int32_t align_corners, void* crops, int32_t out_f16, danet_stream_t stream);
+int danet_stn_sample(int32_t B, int32_t S, int32_t C, const danet_act* xd, const float* theta,
+                     int32_t align_corners, const danet_act* crops, danet_stream_t stream);
 
 /* smpl_regressor.py:858-895 + GCN.py:29-92 + geometry.py:47-61: r2p_gcn -> refine_gcn(+res) ->
  * p2r_gcn -> grouped 1x1 pose head + mean_pose -> rot6d_to_rotmat; also concatenates

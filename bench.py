@@ -23,6 +23,11 @@ LBS_BYTES_PER_BODY = 84460.0                        # SURVEY section 8d compulso
 LBS_FLOP_PER_BODY = 15.8e6
 
 
+def metric_name(batch, width):
+    """ONE metric string for both arms (the driver computes the ratio only when they agree)."""
+    return "images/sec DaNet fwd bs=%d 224x224 (HRNet-W%d + part regressors + SMPL LBS + IUV render)" % (batch, width)
+
+
 def host_threads():
     """Threads for the CPU arms: the cores this process may run on, capped at 32 (oneDNN on small
     batches degrades badly when a 128-core box is oversubscribed)."""
@@ -116,12 +121,14 @@ def cpu_step_factory(width, B, seed=0):
                              smpl_model=model, dp_mesh=mesh)
         m.load_state_dict(synthetic.keyed_state_dict(m.state_dict(), seed))
         m.eval()
-        m._test_ops = TorchEmulOps()
+        emul = TorchEmulOps()
         kind = "port"
         desc = "oracle port: the same graph through torch CPU ops (oracle/net_ops.py)"
 
         def net(x):
-            return m.infer_net(x)["para"]
+            plan = m.plan_for(x.shape[0], "cpu", ops=emul)
+            plan.run(x)
+            return m.outputs_of(plan, x.shape[0])["para"]
 
     from concurrent.futures import ThreadPoolExecutor
     pool = ThreadPoolExecutor(max_workers=min(B, host_threads()))
@@ -155,7 +162,7 @@ def run_reference_arm(args):
     val = n / dt
     cores = host_threads()
     sample = "%d steps x %d images, W%d, %s" % (args.steps, B, args.width, desc)
-    line = {"impl": "reference", "metric": "images/sec DaNet fwd (HRNet-W%d + part regressors + SMPL LBS + IUV render)" % args.width,
+    line = {"impl": "reference", "metric": metric_name(args.batch, args.width),
             "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
@@ -189,8 +196,8 @@ def run_b200_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B, W = args.batch, args.width
-    net = danet_b200.build_synthetic_danet(width=W, seed=0, device=dev, conv_algo=args.conv,
-                                           use_cuda_graph=not args.no_graph, gemm_2x2=not args.no_gemm_2x2)
+    net = danet_b200.build_synthetic_danet(width=W, seed=0, device=dev, conv_algo=args.conv, precision=args.precision,
+                                           use_cuda_graph=not args.no_graph, group_convs=not args.no_group)
     smpl, rend = net.iuv2smpl.smpl, net.iuv_renderer
     nrot = 4                                          # 4 x 38.5 MB input batches > 126 MB L2
     g = torch.Generator().manual_seed(1234 + rank)
@@ -282,7 +289,12 @@ def run_b200_arm(args):
         pk = peaks()
         # ---- per-kernel-class timing of one profiled step (CUDA events on the launch stream) ----
         prof = profile_step(net, plan, dev_in[0], dev)
-        conv_ms = prof["conv_ms"]
+        # the convolutions' time inside the measured (CUDA-graph) step = step time x their share of an eager pass in
+        # which every launch is timed with CUDA events (eager launches do not overlap, the graph's do: the share, not
+        # the absolute eager sum, carries over)
+        eager_total = prof["conv_ms"] + sum(prof["other_ms"].values())
+        conv_share = prof["conv_ms"] / max(1e-9, eager_total)
+        conv_ms = conv_share * (ms / args.steps)
         flops = FLOP_PER_IMG.get(W, 0.0) * B
         conv_tflops = flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         tc_peak = pk["bf16_tflops_sustained"]
@@ -302,21 +314,23 @@ def run_b200_arm(args):
                 "algorithmic_flop_per_launch_group": flops, "conv_ms_per_step": conv_ms,
                 # share within the same eager, individually timed pass (under the CUDA graph + programmatic
                 # dependent launch the step is shorter than the sum of its separately timed launches)
-                "conv_share_of_step": conv_ms / max(1e-9, conv_ms + sum(prof["other_ms"].values())),
-                "eager_sum_vs_graph_step": (conv_ms + sum(prof["other_ms"].values())) / (ms / args.steps),
+                "conv_share_of_step": conv_share, "conv_ms_eager_sum": prof["conv_ms"],
+                "eager_sum_vs_graph_step": eager_total / (ms / args.steps),
+                "precision": plan.precision, "mma_per_k_step": 3 if (plan.n_tc and plan.precision == "exact") else 1,
                 "n_conv_tc": plan.n_tc,
                 "n_conv_total": prof["n_conv"], "other_ms": prof["other_ms"]}
         lbs = lbs_bench(smpl, dev, pk)
         cpu = None
         if world == 1 and not args.no_cpu:
             cpu = cpu_baseline(W, args.cpu_batch)
-        line = {"metric": "images/sec DaNet fwd bs=%d 224x224 (HRNet-W%d + part regressors + SMPL LBS + IUV render)" % (B, W),
+        line = {"metric": metric_name(B, W),
                 "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f16 operands (RN from fp32 activations; conv->conv intermediates stored f16), f32 accumulate" if plan.n_tc else "f32", "data": "synthetic",
+                "dtype": ("split-f16 operands (hi+lo, 22 bits; 3 MMAs per K step), f32 accumulate" if plan.precision == "exact"
+                          else "f16 operands, f32 accumulate") if plan.n_tc else "f32", "data": "synthetic",
                 "config": {"workload": "configs[2]: DaNet forward batch=64 synthetic 224x224, HRNet-W%d + IUV_Renderer" % W,
                            "per_gpu_batch": B, "global_batch": B * world, "parallelism": "image-sharded x%d, one all_gather of para" % world,
-                           "conv_path": "tcgen05 kind::f16 (%d of %d convs) + fp32 FMA" % (plan.n_tc, prof["n_conv"]),
+                           "conv_path": "tcgen05 kind::f16, precision=%s: %d convolutions in %d launches" % (plan.precision, plan.n_tc, prof["n_conv"]),
                            "cuda_graph": not args.no_graph,
                            "l2": "inputs rotate over %d batches (%.0f MB > 126 MB L2); activations (%.1f GB/step) exceed L2"
                                  % (nrot, nrot * B * 3 * 224 * 224 * 4 / 1e6, plan.bytes_alloc / 1e9),
@@ -358,9 +372,13 @@ def profile_step(net, plan, x, dev):
                 e1.record()
                 tag = name
                 if name == "conv2d":
-                    tag = "conv_tc" if a[1] == 1 else "conv_simt"
+                    tag = "conv_simt"
                     d = a[0]
                     shapes.append((tag, d["N"], d["H"], d["Cin"], d["Cout"], d["ksize"], d["stride"], d["wsets"]))
+                elif name == "conv_group":
+                    tag = "conv_tc"
+                    shapes.append(" + ".join("N%d H%d Cin%d Cout%d k%d s%d g%d" % (c["d"]["N"], c["d"]["H"], c["d"]["Cin"], c["d"]["Cout"],
+                                                                             c["d"]["ksize"], c["d"]["stride"], c["d"]["wsets"]) for c in a[0]))
                 events.append((tag, e0, e1))
                 return r
             return wrapped
@@ -377,7 +395,7 @@ def profile_step(net, plan, x, dev):
     ci = 0
     for tag, e0, e1 in events:
         if tag.startswith("conv"):
-            key = "%s N%d H%d Cin%d Cout%d k%d s%d g%d" % shapes[ci]
+            key = shapes[ci] if isinstance(shapes[ci], str) else "%s N%d H%d Cin%d Cout%d k%d s%d g%d" % shapes[ci]
             ent = per_shape.setdefault(key, [0, 0.0])
             ent[0] += 1; ent[1] += e0.elapsed_time(e1)
             ci += 1
@@ -388,7 +406,7 @@ def profile_step(net, plan, x, dev):
     except Exception:
         pass
     n_conv = sum(1 for t, _, _ in events if t.startswith("conv"))
-    kern = "k_conv_tc (tcgen05 f16 -> f32 TMEM) + k_conv_simt" if agg.get("conv_tc") else "k_conv_simt (fp32 FMA implicit GEMM)"
+    kern = "k_conv_tc (tcgen05 kind::f16, TMA tensor-map operands, fp32 TMEM accumulators)" if agg.get("conv_tc") else "k_conv_simt (fp32 FMA implicit GEMM)"
     return {"conv_ms": conv_ms, "n_conv": n_conv, "conv_kernel": kern,
             "other_ms": {k: v for k, v in agg.items() if not k.startswith("conv")},
             "conv_tc_ms": agg.get("conv_tc", 0.0), "conv_simt_ms": agg.get("conv_simt", 0.0)}
@@ -446,8 +464,9 @@ def main():
     ap.add_argument("--conv", default="auto", choices=["auto", "tc", "simt"])
     ap.add_argument("--cpu-batch", type=int, default=4)
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--gemm-2x2", action="store_true", help="(default now) 2x2-pixel 3x3 layers as dense products on the tensor-core path")
-    ap.add_argument("--no-gemm-2x2", action="store_true", help="keep the 2x2-pixel 3x3 layers on the fp32 FMA kernel")
+    ap.add_argument("--precision", default="exact", choices=["exact", "fast"],
+                    help="tensor-core path: exact = split-fp16 operands, 3 MMAs per K step (fp32-grade, default); fast = one fp16 pass")
+    ap.add_argument("--no-group", action="store_true", help="one convolution per launch (no multi-problem launches)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -73,17 +73,17 @@ SIGNATURES = {
     "danet_conv_tc_group": (c_int, [c_int, ctypes.POINTER(ConvProblem), c_p]),
     "danet_act_split": (c_int, [c_i64, c_p, c_p, c_p, c_p]),
     "danet_act_merge": (c_int, [c_i64, c_p, c_p, c_p, c_p]),
-    "danet_nchw_to_nhwc": (c_int, [c_int, c_int, c_int, c_int, c_p, c_p, c_p]),
-    "danet_fuse_sum": (c_int, [c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_int, c_p, c_p]),
-    "danet_maxpool3x3s2": (c_int, [c_int, c_int, c_int, c_int, c_p, c_p, c_p]),
-    "danet_global_avgpool": (c_int, [c_int, c_int, c_int, c_p, c_p, c_p]),
+    "danet_nchw_to_nhwc": (c_int, [c_int, c_int, c_int, c_int, c_p, ctypes.POINTER(Act), c_p]),
+    "danet_fuse_sum": (c_int, [c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(Act), c_p, c_int, ctypes.POINTER(Act), c_p]),
+    "danet_maxpool3x3s2": (c_int, [c_int, c_int, c_int, c_int, ctypes.POINTER(Act), ctypes.POINTER(Act), c_p]),
+    "danet_global_avgpool": (c_int, [c_int, c_int, c_int, ctypes.POINTER(Act), c_p, c_p]),
     "danet_linear": (c_int, [c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_p, c_p]),
     "danet_iuv_clean_global": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                                       c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
+                                       c_p, ctypes.POINTER(Act), c_p, c_p, c_p, c_p, c_p, c_p]),
     "danet_iuvmap_clean_nchw": (c_int, [c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
-    "danet_iuv_clean_parts": (c_int, [c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_int, c_p]),
+    "danet_iuv_clean_parts": (c_int, [c_int, c_int, c_int, c_int, c_p, ctypes.POINTER(Act), c_p, c_p]),
     "danet_stn_params": (c_int, [c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_f, c_int, c_p, c_p, c_p]),
-    "danet_stn_sample": (c_int, [c_int, c_int, c_int, c_p, c_p, c_int, c_p, c_int, c_p]),
+    "danet_stn_sample": (c_int, [c_int, c_int, c_int, ctypes.POINTER(Act), c_p, c_int, ctypes.POINTER(Act), c_p]),
     "danet_gcn_pose_head": (c_int, [c_int, ctypes.POINTER(GcnParams), c_p, c_p, c_p, c_p]),
 }
 

@@ -25,8 +25,9 @@ HR_STAGES = (
 )
 
 
-def pad4(c):
-    return (c + 3) // 4 * 4
+def pad8(c):
+    """Channel padding of NHWC activations: fp16 planes move in 16-byte rows (TMA strides, 8-byte vector access)."""
+    return (c + 7) // 8 * 8
 
 
 class Tensor(object):
@@ -34,7 +35,7 @@ class Tensor(object):
 
     def __init__(self, name, nmult, H, W, C, dtype="f32", raw=False):
         self.name, self.nmult, self.H, self.W, self.C, self.dtype = name, nmult, H, W, C, dtype
-        self.Cp = C if raw else pad4(C)      # raw: small per-sample vectors, no channel padding
+        self.Cp = C if raw else pad8(C)      # raw: small per-sample vectors, no channel padding
 
     def __repr__(self):
         return "T(%s %dx[%d,%d,%d])" % (self.name, self.nmult, self.H, self.W, self.C)

@@ -38,15 +38,19 @@ def gather_outputs(local, n_total, group=None):
     return torch.cat(pieces, 0)
 
 
-def infer_sharded(model, images, group=None):
+def infer_sharded(model, images, group=None, infer=None):
     """Every rank passes the same [N,3,224,224] batch (or its own view of it); returns para [N,229]
-    on every rank."""
+    on every rank.  `infer` (images -> para) defaults to model.infer_net; an empty shard contributes an empty
+    tensor on the MODEL's device (the collective needs one device type on every rank)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     lo, hi = shard_bounds(images.shape[0], world, rank)
     local = images[lo:hi]
+    if infer is None:
+        infer = lambda x: model.infer_net(x)["para"]
     if hi > lo:
-        para = model.infer_net(local)["para"]
+        para = infer(local)
     else:
-        para = torch.zeros(0, 229, device=images.device)
+        dev = next(model.parameters()).device if model is not None else images.device
+        para = torch.zeros(0, 229, device=dev)
     return gather_outputs(para, images.shape[0], group)

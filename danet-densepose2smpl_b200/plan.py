@@ -1,6 +1,8 @@
 """Execution plan of the DaNet network half: folds BatchNorm into the convolutions, packs the
-weights into the kernels' layouts, plans activation buffers (liveness-based reuse) and replays
-the op list through the C ABI (optionally as one CUDA graph)."""
+weights into the kernels' layouts, schedules the graph into launch steps (independent convolutions --
+HRNet's parallel branches, the body / limb regressors -- share one tensor-core launch), plans
+activation buffers (liveness-based reuse) and replays the steps through the C ABI (optionally as one
+CUDA graph)."""
 import ctypes
 
 import numpy as np
@@ -10,6 +12,34 @@ from . import _lib
 from . import netgraph as ng
 
 BN_EPS = 1e-5
+MAX_GROUP = 6            # problems per tensor-core launch (csrc/conv_tc.cu kMaxProb)
+
+
+class ActBuf(object):
+    """One activation tensor of the plan (include/danet_b200.h danet_act): an fp32 NHWC view and/or
+    split-fp16 planes h[P,N,H,W,C] (P = 2: hi + lo, exact mode; P = 1: hi only, fast mode)."""
+    __slots__ = ("f32", "h")
+
+    def __init__(self, f32=None, h=None):
+        self.f32, self.h = f32, h
+
+    def c(self):
+        a = _lib.Act()
+        a.f32 = self.f32.data_ptr() if self.f32 is not None else None
+        a.hi = self.h[0].data_ptr() if self.h is not None else None
+        a.lo = self.h[1].data_ptr() if (self.h is not None and self.h.shape[0] > 1) else None
+        return a
+
+    def value(self):
+        """fp32 torch tensor of the activation (tests / debugging)."""
+        if self.f32 is not None:
+            return self.f32
+        v = self.h[0].float()
+        return v + self.h[1].float() if self.h.shape[0] > 1 else v
+
+
+def _null_act():
+    return _lib.Act(None, None, None)
 
 
 class CudaOps(object):
@@ -21,6 +51,13 @@ class CudaOps(object):
         self.lib = _lib.load()
         self.device = torch.device(device)
 
+    def planes(self, precision):
+        """fp16 planes per activation on the tensor-core path (0 would mean: fp32 buffers only)."""
+        return 2 if precision == "exact" else 1
+
+    def _sp(self):
+        return _lib.stream_ptr(self.device)
+
     @staticmethod
     def _desc(d):
         c = _lib.ConvDesc()
@@ -29,7 +66,9 @@ class CudaOps(object):
         c.flags = int(d.get("flags", 0))
         return c
 
-    supports_f16 = True      # tensor-core convs take / produce fp16 activation buffers (danet_conv_desc.flags)
+    def tc_capable(self):
+        """The tcgen05 kernels are sm_100a code: compute capability 10.x only."""
+        return torch.cuda.get_device_capability(self.device)[0] == 10
 
     def conv_tc_supported(self, d):
         return bool(self.lib.danet_conv_tc_supported(ctypes.byref(self._desc(d))))
@@ -37,65 +76,79 @@ class CudaOps(object):
     def conv_tc_pack(self, d, w_simt):
         c = self._desc(d)
         nbytes = int(self.lib.danet_conv_tc_packed_bytes(ctypes.byref(c)))
+        if nbytes <= 0:
+            raise RuntimeError("danet_b200: convolution %r is not supported by the tensor-core path" % (d,))
         out = torch.empty(nbytes, dtype=torch.uint8, device=w_simt.device)
-        _lib.check(self.lib.danet_conv_tc_pack(ctypes.byref(c), _lib.ptr(w_simt), _lib.ptr(out), _lib.stream_ptr()),
-                   "conv_tc_pack")
+        _lib.check(self.lib.danet_conv_tc_pack(ctypes.byref(c), _lib.ptr(w_simt), _lib.ptr(out), self._sp()), "conv_tc_pack")
         return out
 
-    def conv2d(self, d, algo, x, w, bias, res, y):
-        _lib.check(self.lib.danet_conv2d(ctypes.byref(self._desc(d)), algo, _lib.ptr(x), _lib.ptr(w), _lib.ptr(bias),
-                                         _lib.ptr(res), _lib.ptr(y), _lib.stream_ptr()), "conv2d")
+    def conv_group(self, convs):
+        """convs: list of dict(d, x, res, y (ActBuf), w (packed), b)."""
+        arr = (_lib.ConvProblem * len(convs))()
+        for i, cv in enumerate(convs):
+            p = arr[i]
+            p.d = self._desc(cv["d"])
+            p.x = cv["x"].c()
+            p.res = cv["res"].c() if cv["res"] is not None else _null_act()
+            p.y = cv["y"].c()
+            p.w_packed = cv["w"].data_ptr()
+            p.bias = cv["b"].data_ptr() if cv["b"] is not None else None
+        _lib.check(self.lib.danet_conv_tc_group(len(convs), arr, self._sp()), "conv_tc_group")
+
+    def conv2d(self, d, x, w, bias, res, y):
+        """fp32 FMA convolution on the fp32 views."""
+        _lib.check(self.lib.danet_conv2d(ctypes.byref(self._desc(d)), 0, _lib.ptr(x.f32), _lib.ptr(w), _lib.ptr(bias),
+                                         _lib.ptr(res.f32 if res is not None else None), _lib.ptr(y.f32), self._sp()), "conv2d")
 
     def nchw_to_nhwc(self, x, y):
         N, C, H, W = x.shape
-        _lib.check(self.lib.danet_nchw_to_nhwc(N, C, H * W, y.shape[-1], _lib.ptr(x), _lib.ptr(y), _lib.stream_ptr()),
+        t = y.f32 if y.f32 is not None else y.h[0]
+        _lib.check(self.lib.danet_nchw_to_nhwc(N, C, H * W, t.shape[-1], _lib.ptr(x), ctypes.byref(y.c()), self._sp()),
                    "nchw_to_nhwc")
 
-    def fuse_sum(self, terms, factors, relu, y):
-        N, H, W, C = y.shape
+    def fuse_sum(self, terms, factors, relu, y, shape):
+        N, H, W, C = shape
         n = len(terms)
-        arr = (ctypes.c_void_p * n)(*[t.data_ptr() for t in terms])
+        arr = (_lib.Act * n)(*[t.c() for t in terms])
         fac = (ctypes.c_int32 * n)(*factors)
-        _lib.check(self.lib.danet_fuse_sum(N, H, W, C, n, ctypes.cast(arr, ctypes.c_void_p),
-                                           ctypes.cast(fac, ctypes.c_void_p), int(relu), _lib.ptr(y), _lib.stream_ptr()),
-                   "fuse_sum")
+        _lib.check(self.lib.danet_fuse_sum(N, H, W, C, n, arr, ctypes.cast(fac, ctypes.c_void_p), int(relu),
+                                           ctypes.byref(y.c()), self._sp()), "fuse_sum")
 
-    def maxpool(self, x, y):
-        N, H, W, C = x.shape
-        _lib.check(self.lib.danet_maxpool3x3s2(N, H, W, C, _lib.ptr(x), _lib.ptr(y), _lib.stream_ptr()), "maxpool")
+    def maxpool(self, x, y, shape):
+        N, H, W, C = shape
+        _lib.check(self.lib.danet_maxpool3x3s2(N, H, W, C, ctypes.byref(x.c()), ctypes.byref(y.c()), self._sp()), "maxpool")
 
-    def avgpool(self, x, y):
-        N, H, W, C = x.shape
-        _lib.check(self.lib.danet_global_avgpool(N, H * W, C, _lib.ptr(x), _lib.ptr(y), _lib.stream_ptr()), "avgpool")
+    def avgpool(self, x, y, shape):
+        N, H, W, C = shape
+        _lib.check(self.lib.danet_global_avgpool(N, H * W, C, ctypes.byref(x.c()), _lib.ptr(y), self._sp()), "avgpool")
 
     def linear(self, x, w, b, add, y):
         N, In = x.shape[0], w.shape[1]
         _lib.check(self.lib.danet_linear(N, In, w.shape[0], _lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(add),
-                                         _lib.ptr(y), _lib.stream_ptr()), "linear")
+                                         _lib.ptr(y), self._sp()), "linear")
 
-    def clean_global(self, heads, body, amax, vis):
-        B, H, W, Ch = heads.shape
+    def clean_global(self, heads, body, amax, vis, shape):
+        B, H, W, Ch, Cb = shape
         u, v, i, a = vis if vis is not None else (None, None, None, None)
-        _lib.check(self.lib.danet_iuv_clean_global(B, H * W, Ch, 0, 25, 50, 75, body.shape[-1], _lib.ptr(heads),
-                                                   _lib.ptr(body), _lib.ptr(amax), _lib.ptr(u), _lib.ptr(v), _lib.ptr(i),
-                                                   _lib.ptr(a), _lib.stream_ptr()), "iuv_clean_global")
+        _lib.check(self.lib.danet_iuv_clean_global(B, H * W, Ch, 0, 25, 50, 75, Cb, _lib.ptr(heads.f32),
+                                                   ctypes.byref(body.c()), _lib.ptr(amax), _lib.ptr(u), _lib.ptr(v), _lib.ptr(i),
+                                                   _lib.ptr(a), self._sp()), "iuv_clean_global")
 
-    def clean_parts(self, x, y, raw):
-        N, H, W, Cx = x.shape
-        _lib.check(self.lib.danet_iuv_clean_parts(N, H * W, Cx, y.shape[-1], _lib.ptr(x), _lib.ptr(y), _lib.ptr(raw),
-                                                  int(y.dtype == torch.float16), _lib.stream_ptr()), "iuv_clean_parts")
+    def clean_parts(self, x, y, raw, shape):
+        N, H, W, Cx, Cy = shape
+        _lib.check(self.lib.danet_iuv_clean_parts(N, H * W, Cx, Cy, _lib.ptr(x.f32), ctypes.byref(y.c()), _lib.ptr(raw),
+                                                  self._sp()), "iuv_clean_parts")
 
     def stn_params(self, hm, amax, ratio, offset, vis_thresh, align_corners, centers, theta):
-        B, S, _, Chm = hm.shape
-        _lib.check(self.lib.danet_stn_params(B, S, Chm, _lib.ptr(hm), _lib.ptr(amax), _lib.ptr(ratio), _lib.ptr(offset),
+        B, S, _, Chm = hm.f32.shape
+        _lib.check(self.lib.danet_stn_params(B, S, Chm, _lib.ptr(hm.f32), _lib.ptr(amax), _lib.ptr(ratio), _lib.ptr(offset),
                                              float(vis_thresh), int(align_corners), _lib.ptr(centers), _lib.ptr(theta),
-                                             _lib.stream_ptr()), "stn_params")
+                                             self._sp()), "stn_params")
 
-    def stn_sample(self, xd, theta, align_corners, crops):
-        B, S, _, C = xd.shape
-        _lib.check(self.lib.danet_stn_sample(B, S, C, _lib.ptr(xd), _lib.ptr(theta), int(align_corners),
-                                             _lib.ptr(crops), int(crops.dtype == torch.float16), _lib.stream_ptr()),
-                   "stn_sample")
+    def stn_sample(self, xd, theta, align_corners, crops, shape):
+        B, S, C = shape
+        _lib.check(self.lib.danet_stn_sample(B, S, C, ctypes.byref(xd.c()), _lib.ptr(theta), int(align_corners),
+                                             ctypes.byref(crops.c()), self._sp()), "stn_sample")
 
     def gcn_head(self, gp, rot_feats, gpara, para):
         B = para.shape[0]
@@ -107,7 +160,7 @@ class CudaOps(object):
             p.dim_in[l], p.dim_out[l] = gp["W"][l].shape
         p.head_w = gp["head_w"].data_ptr(); p.head_b = gp["head_b"].data_ptr(); p.mean_pose = gp["mean_pose"].data_ptr()
         _lib.check(self.lib.danet_gcn_pose_head(B, ctypes.byref(p), _lib.ptr(rot_feats), _lib.ptr(gpara), _lib.ptr(para),
-                                                _lib.stream_ptr()), "gcn_pose_head")
+                                                self._sp()), "gcn_pose_head")
 
 
 def fold_bn(sd, prefix, cout):
@@ -143,23 +196,6 @@ def pack_conv(sd, op):
     return wp.reshape(G, k * k * cin_p, cout_p).contiguous(), bp.contiguous()
 
 
-def conv2x2_as_gemm(w, b, cin, cout):
-    """A 3x3 / stride 1 / pad 1 convolution on 2x2-pixel maps touches every input pixel from every output
-    pixel (|dy|,|dx| <= 1 always), so it IS a dense matrix product: x viewed as [images, 4*cin] times
-    W' [4*cin, 4*cout] with W'[(iy,ix,ci), (oy,ox,co)] = w[ky=iy-oy+1, kx=ix-ox+1, ci, co]  (no padding taps:
-    16 of the 36 (tap, pixel) pairs of the direct form multiply zeros).  NHWC memory of x / y / residual is
-    already [image][(y,x,c)], so nothing moves; the images become the pixels of one 1x1 convolution.
-    w [1][9*cin][cout] (SIMT layout), b [1][cout] -> (w' [1][4*cin][4*cout], b' [1][4*cout])."""
-    w9 = w.reshape(3, 3, cin, cout)
-    out = torch.zeros(2, 2, cin, 2, 2, cout, dtype=w.dtype)
-    for iy in range(2):
-        for ix in range(2):
-            for oy in range(2):
-                for ox in range(2):
-                    out[iy, ix, :, oy, ox, :] = w9[iy - oy + 1, ix - ox + 1]
-    return out.reshape(1, 4 * cin, 4 * cout).contiguous(), b.reshape(1, cout).repeat(1, 4).contiguous()
-
-
 def refine_adjacency(sd, rp):
     """normalize_undigraph(I_n + A_mask * relu(edge_importance)) (smpl_regressor.py:870-871,
     utils/graph.py:232-261) -- parameter-only, so evaluated once per weight load."""
@@ -187,124 +223,178 @@ def pack_gcn(sd, rp, device):
     return gp
 
 
+# which views of its input tensors an op needs on the tensor-core path: "h" = fp16 planes, "f" = fp32
+_F32_INPUTS = {("clean_global", "x"), ("clean_parts", "x"), ("stn_params", "hm"), ("gcn_head", "x"), ("gcn_head", "gpara"),
+               ("stn_sample", "theta")}
+
+
+def op_inputs(op):
+    """(tensor, role) pairs an op reads (`amax` / `theta` are outputs of the op that makes them, inputs of the next)."""
+    out = []
+    keys = ["x", "res", "hm", "gpara"]
+    if op["op"] == "stn_params":
+        keys.append("amax")
+    if op["op"] == "stn_sample":
+        keys.append("theta")
+    for key in keys:
+        t = op.get(key)
+        if t is not None:
+            out.append((t, key))
+    for (t, _f) in op.get("terms", []):
+        out.append((t, "term"))
+    return out
+
+
+def op_outputs(op):
+    out = []
+    if op.get("y") is not None:
+        out.append(op["y"])
+    if op["op"] == "clean_global":
+        out.append(op["amax"])
+    if op["op"] == "stn_params":
+        out += [op["theta"], op["centers"]]
+    return out
+
+
 class Plan(object):
     """Compiled forward for a fixed batch size B on one device."""
 
     RP = "iuv2smpl.smpl_para_Outs."
 
-    def __init__(self, graph, state_dict, B, device, conv_algo="simt", align_corners=False, vis_thresh=0.5,
-                 want_vis=True, ops=None, use_cuda_graph=False, f16_intermediates=True, gemm_2x2=False):
+    def __init__(self, graph, state_dict, B, device, conv_algo="simt", precision="exact", align_corners=False,
+                 vis_thresh=0.5, want_vis=True, ops=None, use_cuda_graph=False, group_convs=True, wcache=None):
         self.g, self.B, self.device = graph, B, torch.device(device)
         self.ops = ops if ops is not None else CudaOps(device)
         self.align_corners, self.vis_thresh, self.want_vis = align_corners, vis_thresh, want_vis
-        self.conv_algo = conv_algo
-        self.gemm_2x2 = gemm_2x2          # DaNet passes True; validated by tests/test_kernels_gpu.py, test_net_gpu.py
+        if conv_algo not in ("simt", "tc"):
+            raise ValueError("conv_algo must be 'simt' or 'tc'")
+        if precision not in ("exact", "fast"):
+            raise ValueError("precision must be 'exact' or 'fast'")
+        self.conv_algo, self.precision = conv_algo, precision
+        self.tc = conv_algo == "tc"
+        if self.tc and hasattr(self.ops, "tc_capable") and not self.ops.tc_capable():
+            raise RuntimeError("danet_b200: the tensor-core path is sm_100a code; device %s is not compute capability 10.x" % device)
+        self.P = self.ops.planes(precision) if self.tc else 0          # fp16 planes per activation (0: fp32 buffers only)
+        self.group_convs = group_convs and self.tc
+        self.wcache = wcache if wcache is not None else {}
         self.n_launch = 0
         self.n_tc = 0
         sd = state_dict
         dev = self.device
-        self.steps = []
-        self.f16 = self._f16_tensors() if f16_intermediates else set()
-        self._plan_buffers()
-        for op in graph.ops:
-            kind = op["op"]
-            if kind == "conv":
-                self._add_conv(op, sd)
-            elif kind == "input":
-                self.steps.append(("input", op))
-            elif kind == "fuse":
-                self.steps.append(("fuse", op))
-            elif kind in ("maxpool", "avgpool", "clean_global", "clean_parts", "stn_sample"):
-                self.steps.append((kind, op))
-            elif kind == "stn_params":
-                self.ratio = sd["img2iuv.learned_ratio"].float().contiguous().to(dev)
-                self.offset = sd["img2iuv.learned_offset"].float().contiguous().to(dev)
-                self.steps.append((kind, op))
-            elif kind == "body_fc":
-                self.fc_w = sd[self.RP + "body_net.3.final_layer.weight"].float().contiguous().to(dev)
-                self.fc_b = sd[self.RP + "body_net.3.final_layer.bias"].float().contiguous().to(dev)
-                self.fc_add = sd[self.RP + "mean_cam_shape"].float().reshape(13).contiguous().to(dev)
-                self.pooled = torch.empty(B, 512, device=dev)
-                self.steps.append((kind, op))
-            elif kind == "gcn_head":
-                self.gcn = pack_gcn(sd, self.RP, dev)
-                self.steps.append((kind, op))
-            else:
-                raise ValueError("unknown op %s" % kind)
-        S = graph.outputs["heads"].H
-        self.vis = None
-        self.raw_parts = None
-        if want_vis:
-            self.vis = [torch.empty(B, c, S, S, device=dev) for c in (25, 25, 25, 15)]
-            self.raw_parts = torch.empty(B * 24, 21, S, S, device=dev)
+        with self._guard():
+            self._schedule()
+            self._formats()
+            self._plan_buffers()
+            self.steps = []
+            for level_ops in self.schedule:
+                group = []
+                for op in level_ops:
+                    kind = op["op"]
+                    if kind == "conv":
+                        cv = self._make_conv(op, sd)
+                        if self.tc:
+                            group.append(cv)
+                        else:
+                            self.steps.append(("conv_simt", cv))
+                    else:
+                        self._add_glue(op, sd)
+                # tensor-core convolutions of one level: independent by construction, <= MAX_GROUP per launch,
+                # most expensive tiles first (they start first inside the persistent grid)
+                group.sort(key=lambda c: -c["cost"])
+                gsz = MAX_GROUP if self.group_convs else 1
+                for i in range(0, len(group), gsz):
+                    self.steps.append(("conv_group", group[i:i + gsz]))
+            S = graph.outputs["heads"].H
+            self.vis = None
+            self.raw_parts = None
+            if want_vis:
+                self.vis = [torch.empty(B, c, S, S, device=dev) for c in (25, 25, 25, 15)]
+                self.raw_parts = torch.empty(B * 24, 21, S, S, device=dev)
         self.graph_exec = None
         self.use_cuda_graph = use_cuda_graph
         self.static_in = None
 
-    # tensors callers read after run() (infer_net, tests): never recycled, never fp16
+    def _guard(self):
+        """Kernels, buffers and the stream handle must belong to the plan's device, whatever the caller's
+        current device is."""
+        if self.device.type == "cuda":
+            return torch.cuda.device(self.device)
+        import contextlib
+        return contextlib.nullcontext()
+
+    # tensors callers read after run() (infer_net, tests): never recycled, always with an fp32 view
     KEEP = ("para", "centers", "theta", "amax", "global_para", "rot_feats", "heads", "hm", "body_iuv")
 
     def _keep(self):
         return set(self.g.outputs[k].name for k in self.KEEP if k in self.g.outputs)
 
-    # -- fp16 intermediates -------------------------------------------------------------------
-    def _conv_desc(self, op):
-        x, y = op["x"], op["y"]
-        return dict(N=self.B * x.nmult, H=x.H, W=x.W, Cin=x.Cp, Cout=y.Cp, ksize=op["k"], stride=op["stride"],
-                    pad=op["pad"], wsets=op["groups"], relu=int(op["relu"]))
+    # -- scheduling ---------------------------------------------------------------------------
+    def _schedule(self):
+        """ASAP levels of the op DAG: every op of a level depends only on earlier levels, so the convolutions
+        of a level (HRNet's parallel branches, hr_module.py:165-166; the fuse layers' 1x1 and stride-2
+        convolutions; the body and limb regressors) may share one launch."""
+        level_of_tensor = {}
+        levels = []
+        for op in self.g.ops:
+            lv = 0
+            for (t, _role) in op_inputs(op):
+                lv = max(lv, level_of_tensor.get(t.name, -1) + 1)
+            for t in op_outputs(op):
+                level_of_tensor[t.name] = lv
+            while len(levels) <= lv:
+                levels.append([])
+            levels[lv].append(op)
+        if not self.group_convs:
+            # graph order (one op per step); still expressed as levels
+            levels = [[op] for op in self.g.ops]
+        self.schedule = [l for l in levels if l]
+        self.step_of = {}
+        for idx, l in enumerate(self.schedule):
+            for op in l:
+                self.step_of[id(op)] = idx
 
-    def _f16_tensors(self):
-        """Tensors written by a tensor-core conv and read ONLY as the input of tensor-core convs are kept
-        in fp16: that kernel rounds its activations to fp16 (RN) when it stages them, so the values the
-        MMAs see are bit-identical and the tensor costs half the traffic.  Residuals, fuse terms, glue
-        inputs and graph outputs stay fp32."""
-        if self.conv_algo != "tc" or not getattr(self.ops, "supports_f16", False):
-            return set()
-        tc = {}
-        for op in self.g.ops:
-            if op["op"] == "conv":
-                tc[id(op)] = self.ops.conv_tc_supported(self._conv_desc(op))
-        produced_by_tc, bad = set(), set()
-        for op in self.g.ops:
-            if op["op"] == "conv":
-                if tc[id(op)]:
-                    produced_by_tc.add(op["y"].name)
-                else:
-                    bad.add(op["x"].name)
-                if op["res"] is not None:
-                    bad.add(op["res"].name)
-            else:
-                if op["op"] in ("stn_sample", "clean_parts"):
-                    produced_by_tc.add(op["y"].name)       # these two glue kernels can write fp16 as well
-                for key in ("x", "hm", "amax", "theta", "gpara"):
-                    t = op.get(key)
-                    if t is not None:
-                        bad.add(t.name)
-                for (t, _f) in op.get("terms", []):
-                    bad.add(t.name)
+    # -- tensor formats -----------------------------------------------------------------------
+    def _formats(self):
+        """Views each tensor carries.  fp32 path: fp32 only.  Tensor-core path: convolutions, fuse sums, pools and
+        the STN sampler exchange split-fp16 planes; the kernels that work on fp32 (iuvmap_clean, soft-argmax,
+        GCN head) and the tensors callers read keep an fp32 view."""
+        self.fmt = {}
+        g = self.g
+        for name in g.tensors:
+            self.fmt[name] = set()
         keep = self._keep()
-        out = set()
-        for name in produced_by_tc - bad - keep:
-            t = self.g.tensors[name]
-            if t.Cp % 8 == 0 and t.dtype == "f32":
-                out.add(name)
-        return out
+        for op in g.ops:
+            for (t, role) in op_inputs(op):
+                if t.dtype != "f32":
+                    continue
+                if not self.tc or self.P == 0 or (op["op"], role) in _F32_INPUTS or t.Cp % 8 != 0:
+                    self.fmt[t.name].add("f")
+                else:
+                    self.fmt[t.name].add("h")
+        for name in g.tensors:
+            t = g.tensors[name]
+            if t.dtype != "f32":
+                continue
+            if name in keep or not self.fmt[name]:
+                self.fmt[name].add("f")
+        # producers that can only write fp32
+        for op in g.ops:
+            if op["op"] in ("avgpool", "body_fc", "gcn_head", "stn_params"):
+                for t in op_outputs(op):
+                    if t.dtype == "f32":
+                        if "h" in self.fmt[t.name]:
+                            raise RuntimeError("plan: %s output %s is needed as fp16 planes" % (op["op"], t.name))
 
     # -- buffers ------------------------------------------------------------------------------
     def _plan_buffers(self):
         g, B, dev = self.g, self.B, self.device
-        last_use = {}
-        produced = {}
-        for idx, op in enumerate(g.ops):
-            for key in ("x", "res", "hm", "amax", "theta", "gpara"):
-                t = op.get(key)
-                if t is not None:
-                    last_use[t.name] = idx
-            for (t, _f) in op.get("terms", []):
-                last_use[t.name] = idx
-            for key in ("y", "amax", "theta", "centers"):
-                t = op.get(key)
-                if t is not None and t.name not in produced:
+        last_use, produced = {}, {}
+        for op in g.ops:
+            idx = self.step_of[id(op)]
+            for (t, _r) in op_inputs(op):
+                last_use[t.name] = max(last_use.get(t.name, -1), idx)
+            for t in op_outputs(op):
+                if t.name not in produced:
                     produced[t.name] = idx
         keep = self._keep()
         free = {}
@@ -313,98 +403,141 @@ class Plan(object):
         for name, idx in last_use.items():
             if name not in keep:
                 release_at.setdefault(idx, []).append(name)
-        order = sorted(produced.items(), key=lambda kv: kv[1])
-        oi = 0
-        for idx in range(len(g.ops)):
-            while oi < len(order) and order[oi][1] == idx:
-                name = order[oi][0]
+        by_step = {}
+        for name, idx in produced.items():
+            by_step.setdefault(idx, []).append(name)
+
+        def take(key, maker):
+            pool = free.get(key)
+            return pool.pop() if pool else maker()
+
+        self._pool_key = {}
+        for idx in range(len(self.schedule)):
+            for name in by_step.get(idx, []):
                 t = g.tensors[name]
                 shape = (B * t.nmult, t.H, t.W, t.Cp)
                 numel = int(np.prod(shape))
                 if t.dtype == "u8":
                     self.buf[name] = torch.empty(shape[:3], dtype=torch.uint8, device=dev)
-                elif name in self.f16:
-                    pool = free.get(("h", numel))
-                    self.buf[name] = pool.pop().view(shape) if pool else torch.empty(shape, dtype=torch.float16, device=dev)
-                else:
-                    pool = free.get(numel)
-                    if pool and name not in keep:
-                        self.buf[name] = pool.pop().view(shape)
+                    continue
+                fm = self.fmt[name]
+                f32 = h = None
+                if "f" in fm:
+                    if name in keep:
+                        f32 = torch.empty(shape, device=dev)
                     else:
-                        self.buf[name] = torch.empty(shape, device=dev)
-                oi += 1
+                        f32 = take(("f", numel), lambda: torch.empty(numel, device=dev)).view(shape)
+                if "h" in fm:
+                    h = take(("h", numel), lambda: torch.empty(self.P * numel, dtype=torch.float16, device=dev)).view((self.P,) + shape)
+                    if name in keep:
+                        h = torch.empty((self.P,) + shape, dtype=torch.float16, device=dev)
+                self.buf[name] = ActBuf(f32, h)
             for name in release_at.get(idx, []):
-                t = self.buf.get(name)
-                if t is not None and t.dtype == torch.float32:
-                    free.setdefault(t.numel(), []).append(t)
-                elif t is not None and t.dtype == torch.float16:
-                    free.setdefault(("h", t.numel()), []).append(t)
+                a = self.buf.get(name)
+                if not isinstance(a, ActBuf):
+                    continue
+                if a.f32 is not None:
+                    free.setdefault(("f", a.f32.numel()), []).append(a.f32.reshape(-1))
+                if a.h is not None:
+                    free.setdefault(("h", a.h.numel() // self.P), []).append(a.h.reshape(-1))
         seen = {}
-        for t in self.buf.values():
-            seen[t.untyped_storage().data_ptr()] = t.untyped_storage().nbytes()
+        for a in self.buf.values():
+            for t in ([a] if torch.is_tensor(a) else [a.f32, a.h]):
+                if t is not None:
+                    seen[t.untyped_storage().data_ptr()] = t.untyped_storage().nbytes()
         self.bytes_alloc = sum(seen.values())
 
     def T(self, t):
         return self.buf[t.name]
 
+    def shape(self, t):
+        return (self.B * t.nmult, t.H, t.W, t.Cp)
+
     # -- conv ---------------------------------------------------------------------------------
-    def _add_conv(self, op, sd):
+    def _conv_desc(self, op):
         x, y = op["x"], op["y"]
-        w, b = pack_conv(sd, op)
-        dev = self.device
+        return dict(N=self.B * x.nmult, H=x.H, W=x.W, Cin=x.Cp, Cout=y.Cp, ksize=op["k"], stride=op["stride"],
+                    pad=op["pad"], wsets=op["groups"], relu=int(op["relu"]),
+                    flags=4 if (self.tc and self.precision == "exact") else 0)
+
+    def _make_conv(self, op, sd):
+        x, y = op["x"], op["y"]
         d = self._conv_desc(op)
-        d["flags"] = (1 if x.name in self.f16 else 0) | (2 if y.name in self.f16 else 0)
-        if (self.gemm_2x2 and self.conv_algo == "tc" and d["ksize"] == 3 and d["stride"] == 1 and d["pad"] == 1 and
-                d["H"] == 2 and d["W"] == 2 and d["wsets"] == 1 and d["N"] % 8 == 0 and d["N"] >= 32 and
-                d["flags"] == 0):
-            # the ResNet tail's 2x2-pixel layers as one dense product on the tensor-core path (see
-            # conv2x2_as_gemm); the images become an (N/8) x 8 pixel map of a 1x1 convolution
-            d2 = dict(N=1, H=d["N"] // 8, W=8, Cin=4 * d["Cin"], Cout=4 * d["Cout"], ksize=1, stride=1, pad=0,
-                      wsets=1, relu=d["relu"], flags=0)
-            if self.ops.conv_tc_supported(d2):
-                w, b = conv2x2_as_gemm(w, b, d["Cin"], d["Cout"])
-                d = d2
-        w, b = w.to(dev), b.to(dev)
-        algo = 0
-        if d["flags"] and not self.ops.conv_tc_supported(d):
-            raise RuntimeError("plan: fp16 tensor on a convolution the tensor-core path does not take: %r" % (d,))
-        if self.conv_algo == "tc" and self.ops.conv_tc_supported(d):
-            w = self.ops.conv_tc_pack(d, w)
-            algo = 1
+        dev = self.device
+        key = (op["parts"][0][0], "tc" if self.tc else "simt", d["flags"], x.Cp, y.Cp)
+        if key not in self.wcache:
+            w, b = pack_conv(sd, op)
+            w, b = w.to(dev), b.to(dev)
+            if self.tc:
+                if not self.ops.conv_tc_supported(d):
+                    raise RuntimeError("plan: convolution %r is not supported by the tensor-core path" % (d,))
+                w = self.ops.conv_tc_pack(d, w)
+            self.wcache[key] = (w, b)
+        w, b = self.wcache[key]
+        if self.tc:
             self.n_tc += 1
-        self.steps.append(("conv", dict(d=d, algo=algo, w=w, b=b, x=x, y=y, res=op["res"])))
+        Ho, Wo = y.H, y.W
+        cost = float(d["N"]) * Ho * Wo * d["ksize"] ** 2 * d["Cin"] * d["Cout"]
+        return dict(d=d, w=w, b=b, x=self.T(x), y=self.T(y), res=self.T(op["res"]) if op["res"] is not None else None,
+                    cost=cost, op=op)
+
+    def _add_glue(self, op, sd):
+        kind = op["op"]
+        dev, B = self.device, self.B
+        if kind in ("input", "fuse", "maxpool", "avgpool", "clean_global", "clean_parts", "stn_sample"):
+            self.steps.append((kind, op))
+        elif kind == "stn_params":
+            self.ratio = sd["img2iuv.learned_ratio"].float().contiguous().to(dev)
+            self.offset = sd["img2iuv.learned_offset"].float().contiguous().to(dev)
+            self.steps.append((kind, op))
+        elif kind == "body_fc":
+            self.fc_w = sd[self.RP + "body_net.3.final_layer.weight"].float().contiguous().to(dev)
+            self.fc_b = sd[self.RP + "body_net.3.final_layer.bias"].float().contiguous().to(dev)
+            self.fc_add = sd[self.RP + "mean_cam_shape"].float().reshape(13).contiguous().to(dev)
+            self.pooled = torch.empty(B, 512, device=dev)
+            self.steps.append((kind, op))
+        elif kind == "gcn_head":
+            self.gcn = pack_gcn(sd, self.RP, dev)
+            self.steps.append((kind, op))
+        else:
+            raise ValueError("unknown op %s" % kind)
 
     # -- run ----------------------------------------------------------------------------------
     def _run_steps(self, image):
         ops = self.ops
         n = 0
         for kind, op in self.steps:
-            if kind == "conv":
-                ops.conv2d(op["d"], op["algo"], self.T(op["x"]), op["w"], op["b"],
-                           self.T(op["res"]) if op["res"] is not None else None, self.T(op["y"]))
+            if kind == "conv_group":
+                ops.conv_group(op)
+            elif kind == "conv_simt":
+                ops.conv2d(op["d"], op["x"], op["w"], op["b"], op["res"], op["y"])
             elif kind == "input":
                 ops.nchw_to_nhwc(image, self.T(op["y"]))
             elif kind == "fuse":
-                ops.fuse_sum([self.T(t) for t, _ in op["terms"]], [f for _, f in op["terms"]], op["relu"], self.T(op["y"]))
+                ops.fuse_sum([self.T(t) for t, _ in op["terms"]], [f for _, f in op["terms"]], op["relu"], self.T(op["y"]),
+                             self.shape(op["y"]))
             elif kind == "maxpool":
-                ops.maxpool(self.T(op["x"]), self.T(op["y"]))
+                ops.maxpool(self.T(op["x"]), self.T(op["y"]), self.shape(op["x"]))
             elif kind == "avgpool":
-                ops.avgpool(self.T(op["x"]), self.T(op["y"]))
+                ops.avgpool(self.T(op["x"]), self.T(op["y"]).f32, self.shape(op["x"]))
             elif kind == "clean_global":
-                ops.clean_global(self.T(op["x"]), self.T(op["y"]), self.T(op["amax"]), self.vis)
+                x, y = op["x"], op["y"]
+                ops.clean_global(self.T(x), self.T(y), self.T(op["amax"]), self.vis, (self.B, x.H, x.W, x.Cp, y.Cp))
             elif kind == "stn_params":
                 ops.stn_params(self.T(op["hm"]), self.T(op["amax"]), self.ratio, self.offset, self.vis_thresh,
-                               self.align_corners, self.T(op["centers"]), self.T(op["theta"]))
+                               self.align_corners, self.T(op["centers"]).f32, self.T(op["theta"]).f32)
             elif kind == "stn_sample":
-                ops.stn_sample(self.T(op["x"]), self.T(op["theta"]), self.align_corners, self.T(op["y"]))
+                x = op["x"]
+                ops.stn_sample(self.T(x), self.T(op["theta"]).f32, self.align_corners, self.T(op["y"]), (self.B, x.H, x.Cp))
             elif kind == "clean_parts":
-                ops.clean_parts(self.T(op["x"]), self.T(op["y"]), self.raw_parts)
+                x, y = op["x"], op["y"]
+                ops.clean_parts(self.T(x), self.T(y), self.raw_parts, (self.B * x.nmult, x.H, x.W, x.Cp, y.Cp))
             elif kind == "body_fc":
-                ops.avgpool(self.T(op["x"]), self.pooled)
-                ops.linear(self.pooled, self.fc_w, self.fc_b, self.fc_add, self.T(op["y"]))
+                ops.avgpool(self.T(op["x"]), self.pooled, self.shape(op["x"]))
+                ops.linear(self.pooled, self.fc_w, self.fc_b, self.fc_add, self.T(op["y"]).f32)
                 n += 1
             elif kind == "gcn_head":
-                ops.gcn_head(self.gcn, self.T(op["x"]), self.T(op["gpara"]), self.T(op["y"]))
+                ops.gcn_head(self.gcn, self.T(op["x"]).f32, self.T(op["gpara"]).f32, self.T(op["y"]).f32)
             n += 1
         self.n_launch = n
 
@@ -413,21 +546,25 @@ class Plan(object):
         if image.shape[0] != self.B:
             raise ValueError("plan compiled for batch %d, got %d" % (self.B, image.shape[0]))
         image = image.detach().to(self.device, torch.float32).contiguous()
-        if not self.use_cuda_graph:
-            self._run_steps(image)
-            return
-        if self.graph_exec is None:
-            self.static_in = image.clone()
-            s = torch.cuda.Stream(device=self.device)
-            s.wait_stream(torch.cuda.current_stream(self.device))
-            with torch.cuda.stream(s):
-                self._run_steps(self.static_in)          # warm-up outside capture
-            torch.cuda.current_stream(self.device).wait_stream(s)
-            self.graph_exec = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph_exec):
-                self._run_steps(self.static_in)
-        self.static_in.copy_(image, non_blocking=True)
-        self.graph_exec.replay()
+        with self._guard():
+            if not self.use_cuda_graph:
+                self._run_steps(image)
+                return
+            cur = torch.cuda.current_stream(self.device)
+            if self.graph_exec is None:
+                self.static_in = image.clone()
+                s = torch.cuda.Stream(device=self.device)
+                s.wait_stream(cur)
+                with torch.cuda.stream(s):
+                    self._run_steps(self.static_in)          # warm-up outside capture
+                cur.wait_stream(s)
+                self.graph_exec = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph_exec):
+                    self._run_steps(self.static_in)
+            self.static_in.copy_(image, non_blocking=True)
+            self.graph_exec.replay()
 
     def out(self, name):
-        return self.T(self.g.outputs[name])
+        """fp32 tensor of a graph output."""
+        a = self.T(self.g.outputs[name])
+        return a if torch.is_tensor(a) else a.value()

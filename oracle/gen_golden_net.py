@@ -44,37 +44,51 @@ def top2_margin(x, dim=1):
     return (v.select(dim, 0) - v.select(dim, 1))
 
 
-def gen(ns, width, B, seed):
+def gen(ns, width, B, seed, detail=None, chunk=8):
+    """detail = number of leading images whose per-part maps / sums are stored (all when None); the batch runs
+    through the reference in chunks of `chunk` images (eval-mode network: images are independent)."""
     import torch
     from oracle import ref_import
     est, pred, rsd = build_reference(ns, width, seed)
     img = make_image(torch, B, 100 + seed)
-    r = ref_import.infer_para(ns, est, pred, img)
-    ret = r["ret"]
-    u, v, i, a = r["uvia_clean"]
-    I_raw, A_raw = ret["uvia_pred"][2], ret["uvia_pred"][3]
-    pp = ret["part_iuv_pred"]                                    # [B,24,3,7,56,56]
-    out = dict(
-        para=r["para"].numpy(), stn_kps=ret["stn_kps_pred"].numpy(),
-        index_argmax=I_raw.argmax(1).numpy().astype(np.uint8), index_margin=top2_margin(I_raw).numpy().astype(np.float16),
-        ann_argmax=A_raw.argmax(1).numpy().astype(np.uint8), ann_margin=top2_margin(A_raw).numpy().astype(np.float16),
-        part_argmax=pp[:, :, 2].argmax(2).numpy().astype(np.uint8),
-        part_margin=top2_margin(pp[:, :, 2], dim=2).numpy().astype(np.float16),
-        hm=ret["skps_hm_pred"].numpy().astype(np.float16),
-        u_sum=u.sum(1).numpy().astype(np.float32), v_sum=v.sum(1).numpy().astype(np.float32),
-        part_u_sum=r["part_iuv_map"][:, :, 0].sum(2).numpy().astype(np.float16),
-        heads_sub=torch.cat(ret["uvia_pred"], 1)[:, :, ::4, ::4].numpy().astype(np.float32),
-        parts_sub=pp[:, ::5, :, :, ::8, ::8].numpy().astype(np.float32),
-        width=np.int32(width), B=np.int32(B), seed=np.int32(seed))
-    path = os.path.join(GOLD, "net_w%d.npz" % width)
+    nd = B if detail is None else detail
+    acc = {}
+    for s0 in range(0, B, chunk):
+        r = ref_import.infer_para(ns, est, pred, img[s0:s0 + chunk])
+        ret = r["ret"]
+        u, v, i, a = r["uvia_clean"]
+        I_raw, A_raw = ret["uvia_pred"][2], ret["uvia_pred"][3]
+        pp = ret["part_iuv_pred"]                                    # [b,24,3,7,56,56]
+        part = dict(
+            para=r["para"].numpy(), stn_kps=ret["stn_kps_pred"].numpy(),
+            index_argmax=I_raw.argmax(1).numpy().astype(np.uint8), index_margin=top2_margin(I_raw).numpy().astype(np.float16),
+            ann_argmax=A_raw.argmax(1).numpy().astype(np.uint8), ann_margin=top2_margin(A_raw).numpy().astype(np.float16))
+        if s0 < nd:
+            part.update(
+                part_argmax=pp[:, :, 2].argmax(2).numpy().astype(np.uint8),
+                part_margin=top2_margin(pp[:, :, 2], dim=2).numpy().astype(np.float16),
+                u_sum=u.sum(1).numpy().astype(np.float32), v_sum=v.sum(1).numpy().astype(np.float32))
+            if detail is None:
+                part.update(
+                    hm=ret["skps_hm_pred"].numpy().astype(np.float16),
+                    part_u_sum=r["part_iuv_map"][:, :, 0].sum(2).numpy().astype(np.float16),
+                    heads_sub=torch.cat(ret["uvia_pred"], 1)[:, :, ::4, ::4].numpy().astype(np.float32),
+                    parts_sub=pp[:, ::5, :, :, ::8, ::8].numpy().astype(np.float32))
+        for k, val in part.items():
+            acc.setdefault(k, []).append(val)
+    out = {k: np.concatenate(v, 0) for k, v in acc.items()}
+    out.update(width=np.int32(width), B=np.int32(B), seed=np.int32(seed), detail=np.int32(nd))
+    path = os.path.join(GOLD, "net_w%d.npz" % width if detail is None else "net_w%d_b%d.npz" % (width, B))
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path) // 1024, "KiB; para[0,:6] =", out["para"][0, :6])
     return rsd
 
 
-def main(ns):
+def main(ns, big=True):
     rsd = gen(ns, 32, 2, 0)
     rsd48 = gen(ns, 48, 2, 0)
+    if big:
+        gen(ns, 48, 64, 0, detail=8)                  # BASELINE config 3: the benched configuration
     # the reference's state_dict keys + shapes: the drop-in surface (SURVEY section 8b)
     with open(os.path.join(GOLD, "state_dict_keys_w48.txt"), "w") as f:
         for k, v in rsd48.items():

@@ -17,10 +17,25 @@ SMPL2DP = [[1, 2], [8, 10], [7, 9], [1, 2], [8, 10, 12, 14], [7, 9, 11, 13], [1,
 
 
 class TorchEmulOps(object):
-    def conv_tc_supported(self, d):
-        return False
+    """Same interface as danet_b200.plan.CudaOps; activations arrive as plan.ActBuf objects whose fp32 view is
+    the only one present (planes() == 0)."""
 
-    def conv2d(self, d, algo, x, w, bias, res, y):
+    def planes(self, precision):
+        return 0
+
+    def conv_tc_supported(self, d):
+        return True
+
+    def conv_tc_pack(self, d, w):
+        return w
+
+    def conv_group(self, convs):
+        for cv in convs:
+            self.conv2d(cv["d"], cv["x"], cv["w"], cv["b"], cv["res"], cv["y"])
+
+    def conv2d(self, d, x, w, bias, res, y):
+        x, y = x.f32, y.f32
+        res = res.f32 if res is not None else None
         N, H, W, Cin = x.shape
         k, G = d["ksize"], d["wsets"]
         Cout = d["Cout"]
@@ -37,26 +52,30 @@ class TorchEmulOps(object):
         y.copy_(out)
 
     def nchw_to_nhwc(self, x, y):
+        y = y.f32
         y.zero_()
         y[..., :x.shape[1]] = x.permute(0, 2, 3, 1)
 
-    def fuse_sum(self, terms, factors, relu, y):
+    def fuse_sum(self, terms, factors, relu, y, shape=None):
         acc = None
         for t, f in zip(terms, factors):
+            t = t.f32
             u = t.repeat_interleave(f, dim=1).repeat_interleave(f, dim=2) if f > 1 else t
             acc = u.clone() if acc is None else acc + u
-        y.copy_(torch.relu(acc) if relu else acc)
+        y.f32.copy_(torch.relu(acc) if relu else acc)
 
-    def maxpool(self, x, y):
-        y.copy_(F.max_pool2d(x.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1))
+    def maxpool(self, x, y, shape=None):
+        y.f32.copy_(F.max_pool2d(x.f32.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1))
 
-    def avgpool(self, x, y):
+    def avgpool(self, x, y, shape=None):
+        x = x.f32
         y.reshape(x.shape[0], x.shape[-1]).copy_(x.reshape(x.shape[0], -1, x.shape[-1]).mean(1))
 
     def linear(self, x, w, b, add, y):
         y.reshape(-1)[:x.shape[0] * w.shape[0]].view(x.shape[0], w.shape[0]).copy_(x @ w.t() + b + add)
 
-    def clean_global(self, heads, body, amax, vis):
+    def clean_global(self, heads, body, amax, vis, shape=None):
+        heads, body = heads.f32, body.f32
         U, V, I, A = heads[..., 0:25], heads[..., 25:50], heads[..., 50:75], heads[..., 75:90]
         idx = I.argmax(-1)
         oh = F.one_hot(idx, 25).float()
@@ -70,7 +89,8 @@ class TorchEmulOps(object):
             vis[2].copy_(oh.permute(0, 3, 1, 2))
             vis[3].copy_(F.one_hot(A.argmax(-1), 15).float().permute(0, 3, 1, 2))
 
-    def clean_parts(self, x, y, raw):
+    def clean_parts(self, x, y, raw, shape=None):
+        x, y = x.f32, y.f32
         U, V, I = x[..., 0:7], x[..., 7:14], x[..., 14:21]
         oh = F.one_hot(I.argmax(-1), 7).float()
         y.zero_()
@@ -79,6 +99,7 @@ class TorchEmulOps(object):
             raw.copy_(x[..., :21].permute(0, 3, 1, 2))
 
     def stn_params(self, hm, amax, ratio, offset, vis_thresh, align_corners, centers, theta):
+        hm = hm.f32
         B, S = hm.shape[0], hm.shape[1]
         h = hm[..., :24].permute(0, 3, 1, 2).reshape(B, 24, -1)
         p = F.softmax(10 * h, 2).reshape(B, 24, S, S)
@@ -108,7 +129,8 @@ class TorchEmulOps(object):
         centers.reshape(-1)[:B * 48].copy_(c.reshape(-1))
         theta.reshape(-1)[:B * 72].copy_(th.reshape(-1))
 
-    def stn_sample(self, xd, theta, align_corners, crops):
+    def stn_sample(self, xd, theta, align_corners, crops, shape=None):
+        xd, crops = xd.f32, crops.f32
         B, S, _, C = xd.shape
         th = theta.reshape(-1)[:B * 72].view(B, 24, 3)
         x = xd.permute(0, 3, 1, 2)

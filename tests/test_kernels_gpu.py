@@ -38,40 +38,96 @@ CONV_CASES = [
 ]
 
 
-def _conv_case(case, algo, tol):
-    N, H, W, Cin, Cout, k, s, G, relu, has_res = case
-    ops, ref = _ops(), TorchEmulOps()
-    g = torch.Generator().manual_seed(hash(case) & 0xFFFF)
-    d = dict(N=N, H=H, W=W, Cin=Cin, Cout=Cout, ksize=k, stride=s, pad=k // 2, wsets=G, relu=relu)
-    Ho, Wo = (H + 2 * (k // 2) - k) // s + 1, (W + 2 * (k // 2) - k) // s + 1
-    x = torch.randn(N, H, W, Cin, generator=g)
-    w = torch.randn(G, k * k * Cin, Cout, generator=g) * (1.0 / (k * k * Cin)) ** 0.5
-    b = torch.randn(G, Cout, generator=g) * 0.1
-    res = torch.randn(N, Ho, Wo, Cout, generator=g) if has_res else None
-    y_ref = torch.empty(N, Ho, Wo, Cout)
-    ref.conv2d(d, 0, x, w, b, res, y_ref)
-    xc, wc, bc = x.to(DEV), w.to(DEV), b.to(DEV)
-    rc = res.to(DEV) if has_res else None
-    y = torch.full((N, Ho, Wo, Cout), float("nan"), device=DEV)
-    if algo == 1:
-        if not ops.conv_tc_supported(d):
-            pytest.skip("shape not on the tcgen05 path")
-        wc = ops.conv_tc_pack(d, wc)
-    ops.conv2d(d, algo, xc, wc, bc, rc, y)
-    torch.cuda.synchronize()
-    err = (y.cpu() - y_ref).abs().max().item()
-    assert err < tol, (case, err)
+def A(t):
+    """fp32 tensor -> plan.ActBuf with only the fp32 view."""
+    from danet_b200.plan import ActBuf
+    return ActBuf(f32=t)
+
+
+def H(x, planes=2):
+    """fp32 cuda tensor -> plan.ActBuf with split-fp16 planes only (through danet_act_split)."""
+    from danet_b200.plan import ActBuf
+    from conv_tc_common import split
+    hi, lo = split(x, want_lo=planes == 2)
+    return ActBuf(h=torch.stack([hi, lo]) if planes == 2 else hi[None])
+
+
+def Hempty(shape, planes=2):
+    from danet_b200.plan import ActBuf
+    return ActBuf(h=torch.full((planes,) + tuple(shape), float("nan"), dtype=torch.float16, device=DEV))
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
 def test_conv_simt(case):
-    _conv_case(case, 0, 2e-5)
+    N, H_, W, Cin, Cout, k, s, G, relu, has_res = case
+    ops, ref = _ops(), TorchEmulOps()
+    g = torch.Generator().manual_seed(hash(case) & 0xFFFF)
+    d = dict(N=N, H=H_, W=W, Cin=Cin, Cout=Cout, ksize=k, stride=s, pad=k // 2, wsets=G, relu=relu)
+    Ho, Wo = (H_ + 2 * (k // 2) - k) // s + 1, (W + 2 * (k // 2) - k) // s + 1
+    x = torch.randn(N, H_, W, Cin, generator=g)
+    w = torch.randn(G, k * k * Cin, Cout, generator=g) * (1.0 / (k * k * Cin)) ** 0.5
+    b = torch.randn(G, Cout, generator=g) * 0.1
+    res = torch.randn(N, Ho, Wo, Cout, generator=g) if has_res else None
+    y_ref = torch.empty(N, Ho, Wo, Cout)
+    ref.conv2d(d, A(x), w, b, A(res) if has_res else None, A(y_ref))
+    y = torch.full((N, Ho, Wo, Cout), float("nan"), device=DEV)
+    ops.conv2d(d, A(x.to(DEV)), w.to(DEV), b.to(DEV), A(res.to(DEV)) if has_res else None, A(y))
+    torch.cuda.synchronize()
+    err = (y.cpu() - y_ref).abs().max().item()
+    assert err < 2e-5, (case, err)
 
 
-@pytest.mark.parametrize("case", CONV_CASES)
-def test_conv_tc(case):
-    # fp16 operands (10-bit mantissa, RN from fp32), fp32 accumulate
-    _conv_case(case, 1, 8e-3)
+# the tensor-core kernel needs channel counts that are multiples of 8 (the graph pads to 8)
+TC_CASES = [c for c in CONV_CASES if c[3] % 8 == 0 and c[4] % 8 == 0] + [
+    (1, 224, 224, 8, 64, 3, 2, 1, 1, 0),          # the stem: 3 (padded to 8) -> 64, stride 2
+    (48, 2, 2, 128, 128, 3, 1, 24, 1, 1),         # limb_reslayer: 2x2 maps, 24 weight sets
+    (2, 2, 2, 512, 512, 3, 1, 1, 1, 1),           # body_net layer4: 2x2 maps
+    (2, 16, 8, 16, 16, 1, 1, 1, 0, 0),            # a single tile, a single K step
+    (5, 13, 9, 24, 40, 3, 1, 1, 1, 1),            # ragged: nothing divides the tile sizes
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+@pytest.mark.parametrize("exact", [1, 0])
+def test_conv_tc(case, exact):
+    """exact: split-fp16 operands, 3 MMAs -> fp32-grade (the residual is the tensor core's truncating fp32
+    accumulation, growing with K); fast: single fp16 pass (10-bit mantissa operands)."""
+    from conv_tc_common import run_case
+    K = case[5] * case[5] * case[3]
+    y, ym, ref = run_case(case, bool(exact), res_as_planes=bool(hash(case) & 1))
+    tol = (2e-5 + 1.5e-8 * K) if exact else 1.5e-2
+    e1, e2 = (y.double() - ref).abs().max().item(), (ym.double() - ref).abs().max().item()
+    assert not torch.isnan(y).any() and e1 < tol and e2 < tol, (case, exact, e1, e2)
+
+
+def test_conv_tc_multi_problem_launch():
+    """Several independent convolutions (HRNet's branches at one depth: different resolutions, channel counts,
+    one with a residual, one stride-2) in ONE launch == each launched alone, bit for bit."""
+    from conv_tc_common import desc, launch, make_case, merge, pack, problem, split
+    cases = [(2, 56, 56, 48, 48, 3, 1, 1, 1, 1), (2, 28, 28, 96, 96, 3, 1, 1, 1, 0), (2, 14, 14, 192, 192, 3, 1, 1, 0, 1),
+             (2, 7, 7, 384, 384, 3, 1, 1, 1, 1), (2, 56, 56, 48, 96, 3, 2, 1, 0, 0), (2, 14, 14, 192, 48, 1, 1, 1, 0, 0)]
+    for exact in (True, False):
+        probs, outs, keep = [], [], []
+        for c in cases:
+            N, Hh, W, Cin, Cout, k, s, G, relu, has_res = c
+            x, w, b, res = make_case(c, seed=3)
+            d = desc(c, exact)
+            xp = split(x.to(DEV), want_lo=exact)
+            wpk, bc = pack(d, w.to(DEV)), b.to(DEV)
+            rp = split(res.to(DEV), want_lo=exact) if has_res else None
+            Ho, Wo = (Hh + 2 * (k // 2) - k) // s + 1, (W + 2 * (k // 2) - k) // s + 1
+            mk = lambda: (torch.full((N, Ho, Wo, Cout), float("nan"), dtype=torch.float16, device=DEV),
+                          torch.full((N, Ho, Wo, Cout), float("nan"), dtype=torch.float16, device=DEV) if exact else None)
+            y_group, y_single = mk(), mk()
+            probs.append(problem(d, xp, wpk, bc, res_planes=rp, y_planes=y_group))
+            launch([problem(d, xp, wpk, bc, res_planes=rp, y_planes=y_single)])
+            outs.append((y_group, y_single))
+            keep.append((xp, wpk, bc, rp))
+        launch(probs)
+        torch.cuda.synchronize()
+        for (yg, ys), c in zip(outs, cases):
+            assert torch.equal(yg[0], ys[0]) and (not exact or torch.equal(yg[1], ys[1])), (c, exact)
+            assert not torch.isnan(merge(*yg)).any()
 
 
 def test_conv_rejects_bad_arguments():
@@ -79,7 +135,11 @@ def test_conv_rejects_bad_arguments():
     d = dict(N=1, H=8, W=8, Cin=3, Cout=8, ksize=3, stride=1, pad=1, wsets=1, relu=0)
     x = torch.zeros(1, 8, 8, 3, device=DEV)
     with pytest.raises(RuntimeError):
-        ops.conv2d(d, 0, x, x, None, None, x)        # Cin % 4 != 0
+        ops.conv2d(d, A(x), x, None, None, A(x))        # Cin % 4 != 0
+    d = dict(N=1, H=8, W=8, Cin=12, Cout=8, ksize=3, stride=1, pad=1, wsets=1, relu=0)
+    assert not ops.conv_tc_supported(d)                 # tensor-core path: channels must be multiples of 8
+    with pytest.raises(RuntimeError):
+        ops.conv_tc_pack(d, torch.zeros(1, 108, 8, device=DEV))
 
 
 def test_glue_kernels_vs_torch():
@@ -88,68 +148,94 @@ def test_glue_kernels_vs_torch():
     B, S, C = 3, 56, 48
     # fuse_sum with upsampling
     t0, t1, t2 = torch.randn(B, 28, 28, C, generator=g), torch.randn(B, 14, 14, C, generator=g), torch.randn(B, 7, 7, C, generator=g)
-    y_ref = torch.empty(B, 28, 28, C); ref.fuse_sum([t0, t1, t2], [1, 2, 4], True, y_ref)
-    y = torch.empty(B, 28, 28, C, device=DEV); ops.fuse_sum([t0.to(DEV), t1.to(DEV), t2.to(DEV)], [1, 2, 4], True, y)
+    y_ref = torch.empty(B, 28, 28, C); ref.fuse_sum([A(t0), A(t1), A(t2)], [1, 2, 4], True, A(y_ref))
+    y = torch.empty(B, 28, 28, C, device=DEV)
+    ops.fuse_sum([A(t0.to(DEV)), A(t1.to(DEV)), A(t2.to(DEV))], [1, 2, 4], True, A(y), (B, 28, 28, C))
     assert torch.equal(y.cpu(), y_ref)
+    # split-fp16 planes in, planes + fp32 out: the planes carry 22 bits of every value
+    from danet_b200.plan import ActBuf
+    yh = Hempty((B, 28, 28, C)); yh.f32 = torch.empty(B, 28, 28, C, device=DEV)
+    ops.fuse_sum([H(t0.to(DEV)), H(t1.to(DEV)), H(t2.to(DEV))], [1, 2, 4], True, yh, (B, 28, 28, C))
+    assert (yh.f32.cpu() - y_ref).abs().max() < 4e-6
+    assert (ActBuf(h=yh.h).value().cpu() - yh.f32.cpu()).abs().max() < 2e-6
+    yh1 = Hempty((B, 28, 28, C), planes=1)
+    ops.fuse_sum([H(t0.to(DEV), 1), H(t1.to(DEV), 1), A(t2.to(DEV))], [1, 2, 4], True, yh1, (B, 28, 28, C))
+    want = torch.relu(t0.half().float() + t1.half().float().repeat_interleave(2, 1).repeat_interleave(2, 2)
+                      + t2.repeat_interleave(4, 1).repeat_interleave(4, 2)).half()
+    assert (yh1.h[0].cpu().float() - want.float()).abs().max() < 4e-3
     # maxpool / avgpool / linear / nchw->nhwc
     x = torch.randn(B, 28, 28, 64, generator=g)
-    y_ref = torch.empty(B, 14, 14, 64); ref.maxpool(x, y_ref)
-    y = torch.empty(B, 14, 14, 64, device=DEV); ops.maxpool(x.to(DEV), y)
+    y_ref = torch.empty(B, 14, 14, 64); ref.maxpool(A(x), A(y_ref))
+    y = torch.empty(B, 14, 14, 64, device=DEV); ops.maxpool(A(x.to(DEV)), A(y), (B, 28, 28, 64))
     assert torch.equal(y.cpu(), y_ref)
+    yh = Hempty((B, 14, 14, 64)); ops.maxpool(H(x.to(DEV)), yh, (B, 28, 28, 64))
+    assert (yh.value().cpu() - y_ref).abs().max() < 2e-6
     x = torch.randn(B, 2, 2, 512, generator=g)
-    y_ref = torch.empty(B, 512); ref.avgpool(x, y_ref)
-    y = torch.empty(B, 512, device=DEV); ops.avgpool(x.to(DEV), y)
+    y_ref = torch.empty(B, 512); ref.avgpool(A(x), y_ref)
+    y = torch.empty(B, 512, device=DEV); ops.avgpool(A(x.to(DEV)), y, (B, 2, 2, 512))
     assert (y.cpu() - y_ref).abs().max() < 1e-6
+    y2 = torch.empty(B, 512, device=DEV); ops.avgpool(H(x.to(DEV)), y2, (B, 2, 2, 512))
+    assert (y2.cpu() - y_ref).abs().max() < 2e-6
     w, b, add = torch.randn(13, 512, generator=g), torch.randn(13, generator=g), torch.randn(13, generator=g)
     o_ref = torch.empty(B, 13); ref.linear(y_ref, w, b, add, o_ref)
     o = torch.empty(B, 13, device=DEV); ops.linear(y, w.to(DEV), b.to(DEV), add.to(DEV), o)
     assert (o.cpu() - o_ref).abs().max() < 1e-4
     img = torch.randn(B, 3, 20, 20, generator=g)
-    n_ref = torch.empty(B, 20, 20, 4); ref.nchw_to_nhwc(img, n_ref)
-    n = torch.empty(B, 20, 20, 4, device=DEV); ops.nchw_to_nhwc(img.to(DEV), n)
+    n_ref = torch.empty(B, 20, 20, 8); ref.nchw_to_nhwc(img, A(n_ref))
+    n = torch.empty(B, 20, 20, 8, device=DEV); ops.nchw_to_nhwc(img.to(DEV), A(n))
     assert torch.equal(n.cpu(), n_ref)
+    nh = Hempty((B, 20, 20, 8)); ops.nchw_to_nhwc(img.to(DEV), nh)
+    assert (nh.value().cpu() - n_ref).abs().max() < 2e-6 and torch.equal(nh.h[0].cpu(), n_ref.half())
 
 
 def test_clean_and_stn_kernels_vs_torch():
     ops, ref = _ops(), TorchEmulOps()
     g = torch.Generator().manual_seed(8)
     B, S, C = 3, 56, 48
-    heads = torch.randn(B, S, S, 92, generator=g)
+    heads = torch.randn(B, S, S, 96, generator=g)
     heads[0, 0, 0, 50:75] = 1.0                      # exact tie -> first index
-    body_r, amax_r = torch.empty(B, S, S, 76), torch.empty(B, S, S, dtype=torch.uint8)
+    body_r, amax_r = torch.empty(B, S, S, 80), torch.empty(B, S, S, dtype=torch.uint8)
     vis_r = [torch.empty(B, c, S, S) for c in (25, 25, 25, 15)]
-    ref.clean_global(heads, body_r, amax_r, vis_r)
-    body, amax = torch.empty(B, S, S, 76, device=DEV), torch.empty(B, S, S, dtype=torch.uint8, device=DEV)
+    ref.clean_global(A(heads), A(body_r), amax_r, vis_r)
+    body, amax = torch.empty(B, S, S, 80, device=DEV), torch.empty(B, S, S, dtype=torch.uint8, device=DEV)
     vis = [torch.empty(B, c, S, S, device=DEV) for c in (25, 25, 25, 15)]
-    ops.clean_global(heads.to(DEV), body, amax, vis)
+    bb = Hempty((B, S, S, 80)); bb.f32 = body
+    ops.clean_global(A(heads.to(DEV)), bb, amax, vis, (B, S, S, 96, 80))
     assert torch.equal(amax.cpu(), amax_r) and torch.equal(body.cpu(), body_r)
+    from danet_b200.plan import ActBuf
+    assert (ActBuf(h=bb.h).value().cpu() - body_r).abs().max() < 2e-6          # fp32 view and planes written together
     for a, b in zip(vis, vis_r):
         assert torch.equal(a.cpu(), b)
     x = torch.randn(B * 24, S, S, 24, generator=g)
     y_r, raw_r = torch.empty(B * 24, S, S, 24), torch.empty(B * 24, 21, S, S)
-    ref.clean_parts(x, y_r, raw_r)
+    ref.clean_parts(A(x), A(y_r), raw_r)
     y, raw = torch.empty(B * 24, S, S, 24, device=DEV), torch.empty(B * 24, 21, S, S, device=DEV)
-    ops.clean_parts(x.to(DEV), y, raw)
+    ops.clean_parts(A(x.to(DEV)), A(y), raw, (B * 24, S, S, 24, 24))
     assert torch.equal(y.cpu(), y_r) and torch.equal(raw.cpu(), raw_r)
-    y16 = torch.full((B * 24, S, S, 24), float("nan"), dtype=torch.float16, device=DEV)      # fp16 output option
-    ops.clean_parts(x.to(DEV), y16, None)
-    assert torch.equal(y16.cpu(), y_r.to(torch.float16))
+    y16 = Hempty((B * 24, S, S, 24))                                                            # split-fp16 planes
+    ops.clean_parts(A(x.to(DEV)), y16, None, (B * 24, S, S, 24, 24))
+    assert torch.equal(y16.h[0].cpu(), y_r.to(torch.float16)) and (y16.value().cpu() - y_r).abs().max() < 2e-6
     # stn params + sampling, both align_corners conventions
     hm = torch.randn(B, S, S, 24, generator=g) * 0.3
     ratio, offset = torch.rand(24, generator=g) + 0.5, torch.rand(24, generator=g) * 0.2
     xd = torch.randn(B, S, S, C, generator=g)
     for ac in (0, 1):
         c_r, th_r = torch.empty(B, 1, 24, 2), torch.empty(B, 1, 24, 3)
-        ref.stn_params(hm, amax_r, ratio, offset, 0.5, ac, c_r, th_r)
+        ref.stn_params(A(hm), amax_r, ratio, offset, 0.5, ac, c_r, th_r)
         c, th = torch.empty(B, 1, 24, 2, device=DEV), torch.empty(B, 1, 24, 3, device=DEV)
-        ops.stn_params(hm.to(DEV), amax, ratio.to(DEV), offset.to(DEV), 0.5, ac, c, th)
+        ops.stn_params(A(hm.to(DEV)), amax, ratio.to(DEV), offset.to(DEV), 0.5, ac, c, th)
         assert (c.cpu() - c_r).abs().max() < 2e-5 and (th.cpu() - th_r).abs().max() < 2e-5
-        crops_r = torch.empty(B * 24, S, S, C); ref.stn_sample(xd, th_r, ac, crops_r)
-        crops = torch.empty(B * 24, S, S, C, device=DEV); ops.stn_sample(xd.to(DEV), th_r.to(DEV), ac, crops)
+        crops_r = torch.empty(B * 24, S, S, C); ref.stn_sample(A(xd), th_r, ac, A(crops_r))
+        crops = torch.empty(B * 24, S, S, C, device=DEV)
+        ops.stn_sample(A(xd.to(DEV)), th_r.to(DEV), ac, A(crops), (B, S, C))
         assert (crops.cpu() - crops_r).abs().max() < 2e-4
-        crops16 = torch.full((B * 24, S, S, C), float("nan"), dtype=torch.float16, device=DEV)
-        ops.stn_sample(xd.to(DEV), th_r.to(DEV), ac, crops16)
-        assert torch.equal(crops16, crops.to(torch.float16))           # same values, RN-rounded
+        crops16 = Hempty((B * 24, S, S, C))
+        ops.stn_sample(A(xd.to(DEV)), th_r.to(DEV), ac, crops16, (B, S, C))
+        assert torch.equal(crops16.h[0], crops.to(torch.float16))           # same values, RN-rounded
+        assert (crops16.value() - crops).abs().max() < 2e-6
+        crops_h = Hempty((B * 24, S, S, C))                                  # planes in, planes out
+        ops.stn_sample(H(xd.to(DEV)), th_r.to(DEV), ac, crops_h, (B, S, C))
+        assert (crops_h.value() - crops).abs().max() < 4e-6
 
 
 def test_gcn_pose_head_vs_torch():
@@ -172,73 +258,3 @@ def test_gcn_pose_head_vs_torch():
     gpc = {k: ([t.to(DEV) for t in v] if isinstance(v, list) else v.to(DEV)) for k, v in gp.items()}
     p = torch.empty(B, 1, 1, 229, device=DEV); ops.gcn_head(gpc, rot.to(DEV), gpara.to(DEV), p)
     assert (p.cpu() - p_ref).abs().max() < 5e-5
-
-
-F16_CASES = [
-    # N, H, W, C1, C2, C3, k, stride
-    (2, 56, 56, 48, 48, 48, 3, 1),
-    (3, 13, 9, 24, 40, 16, 3, 1),          # ragged tiles, narrow channel counts
-    (2, 28, 28, 64, 64, 128, 3, 2),        # fp16 input through the stride-2 parity planes
-    (2, 20, 20, 24, 64, 64, 7, 2),         # limb_net.0 -> conv1 pattern (1x1 then 7x7 stride 2)
-]
-
-
-@pytest.mark.parametrize("case", F16_CASES)
-def test_conv_tc_f16_intermediate_is_bit_identical(case):
-    """y = conv2(conv1(x)): storing the intermediate as fp16 (DANET_CONV_Y_F16 / _X_F16) must give the
-    same bits as the fp32 intermediate, because the kernel rounds its activations to fp16 (RN) either way."""
-    N, H, W, C1, C2, C3, k, s = case
-    ops = _ops()
-    g = torch.Generator().manual_seed(7)
-    x = torch.randn(N, H, W, C1, generator=g).to(DEV)
-    k1 = 1 if k == 7 else 3
-    d1 = dict(N=N, H=H, W=W, Cin=C1, Cout=C2, ksize=k1, stride=1, pad=k1 // 2, wsets=1, relu=1)
-    Ho = (H + 2 * (k // 2) - k) // s + 1
-    Wo = (W + 2 * (k // 2) - k) // s + 1
-    d2 = dict(N=N, H=H, W=W, Cin=C2, Cout=C3, ksize=k, stride=s, pad=k // 2, wsets=1, relu=0)
-    w1 = (torch.randn(1, k1 * k1 * C1, C2, generator=g) * 0.1).to(DEV)
-    w2 = (torch.randn(1, k * k * C2, C3, generator=g) * 0.05).to(DEV)
-    b1 = (torch.randn(1, C2, generator=g) * 0.1).to(DEV)
-    b2 = (torch.randn(1, C3, generator=g) * 0.1).to(DEV)
-    res = torch.randn(N, Ho, Wo, C3, generator=g).to(DEV)
-    p1, p2 = ops.conv_tc_pack(d1, w1), ops.conv_tc_pack(d2, w2)
-    # fp32 intermediate
-    t32 = torch.empty(N, H, W, C2, device=DEV)
-    y32 = torch.empty(N, Ho, Wo, C3, device=DEV)
-    ops.conv2d(d1, 1, x, p1, b1, None, t32)
-    ops.conv2d(d2, 1, t32, p2, b2, res, y32)
-    # fp16 intermediate
-    t16 = torch.full((N, H, W, C2), float("nan"), dtype=torch.float16, device=DEV)
-    y16 = torch.empty(N, Ho, Wo, C3, device=DEV)
-    ops.conv2d(dict(d1, flags=2), 1, x, p1, b1, None, t16)
-    ops.conv2d(dict(d2, flags=1), 1, t16, p2, b2, res, y16)
-    torch.cuda.synchronize()
-    assert torch.equal(t16, t32.to(torch.float16))       # same RN rounding as torch
-    assert torch.equal(y16, y32)
-    # the fp32 FMA path refuses fp16 tensors
-    with pytest.raises(RuntimeError):
-        ops.conv2d(dict(d1, flags=2), 0, x, w1, b1, None, t16)
-
-
-def test_conv2x2_as_gemm_on_the_tensor_core_path():
-    """plan.conv2x2_as_gemm: the ResNet tail's 3x3 convolutions on 2x2-pixel maps as ONE dense product through the
-    tcgen05 kernel (images = pixels of a 1x1 convolution, nothing moves in memory) vs the exact fp32 kernel."""
-    from danet_b200.plan import conv2x2_as_gemm
-    ops = _ops()
-    g = torch.Generator().manual_seed(21)
-    N, C = 64, 512
-    x = torch.randn(N, 2, 2, C, generator=g).to(DEV)
-    w = (torch.randn(1, 9 * C, C, generator=g) * 0.02)
-    b = torch.randn(1, C, generator=g) * 0.1
-    res = torch.randn(N, 2, 2, C, generator=g).to(DEV)
-    d = dict(N=N, H=2, W=2, Cin=C, Cout=C, ksize=3, stride=1, pad=1, wsets=1, relu=1)
-    y_ref = torch.empty(N, 2, 2, C, device=DEV)
-    ops.conv2d(d, 0, x, w.to(DEV), b.to(DEV), res, y_ref)
-    d2 = dict(N=1, H=N // 8, W=8, Cin=4 * C, Cout=4 * C, ksize=1, stride=1, pad=0, wsets=1, relu=1)
-    assert ops.conv_tc_supported(d2)
-    w2, b2 = conv2x2_as_gemm(w, b, C, C)
-    y = torch.full((N, 2, 2, C), float("nan"), device=DEV)
-    ops.conv2d(d2, 1, x, ops.conv_tc_pack(d2, w2.to(DEV)), b2.to(DEV), res, y)
-    torch.cuda.synchronize()
-    err = (y - y_ref).abs().max().item() / y_ref.abs().max().item()
-    assert err < 8e-3, err

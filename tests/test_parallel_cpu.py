@@ -19,11 +19,11 @@ def _worker(rank, world, port, tmp):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.set_num_threads(2)
     from danet_b200 import parallel
-    from net_common import build, make_image
+    from net_common import build, infer_with_ops, make_image
     from oracle.net_ops import TorchEmulOps
-    net = build(32, ops=TorchEmulOps())
+    net, emul = build(32), TorchEmulOps()
     img = make_image(3, 100)                     # 3 images over 2 ranks: ragged shards (2 + 1)
-    para = parallel.infer_sharded(net, img)
+    para = parallel.infer_sharded(net, img, infer=lambda x: infer_with_ops(net, x, emul)["para"])
     if rank == 0:
         torch.save(para, tmp)
     dist.barrier()
@@ -43,12 +43,11 @@ def test_shard_bounds():
 
 def test_two_rank_gloo_matches_single_process(tmp_path):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from net_common import build, make_image
+    from net_common import build, infer_with_ops, make_image
     from oracle.net_ops import TorchEmulOps
     out = str(tmp_path / "para.pt")
     mp.spawn(_worker, args=(2, 29541, out), nprocs=2, join=True)
     got = torch.load(out)
-    net = build(32, ops=TorchEmulOps())
-    want = net.infer_net(make_image(3, 100))["para"]
+    want = infer_with_ops(build(32), make_image(3, 100), TorchEmulOps())["para"]
     assert got.shape == (3, 229)
     assert (got - want).abs().max() < 1e-5

@@ -110,7 +110,8 @@ def cpu_step_factory(width, B, seed=0):
             ns = ref_import.load(width)
             est, pred, _ = gen_golden_net.build_reference(ns, width, seed)
         kind = "reference"
-        desc = "reference modules (IUV_Estimator + iuvmap_clean + DecomposedPredictor) imported from /root/reference"
+        desc = ("the reference's own modules (IUV_Estimator + iuvmap_clean + DecomposedPredictor) imported from %s" %
+                ("/root/reference" if ref_import.REF.startswith("/root/reference") else "oracle/_ref (oracle/make_ref.py)"))
 
         def net(x):
             return ref_import.infer_para(ns, est, pred, x)["para"]

@@ -57,9 +57,10 @@ struct alignas(64) Prob {
     int TG;                              // filter taps per weight block
     int NT, ntn;                         // output channels per N tile, N tiles
     int nconcat;                         // exact mode: hi and lo weight rows share one block (one MMA of width 2*NT)
-    int wsplit;                          // exact mode without nconcat: hi and lo rows are separate blocks
     int ACC;                             // accumulator columns per sub-tile
     int big;                             // S*ACC > 256: the tile takes both accumulator halves
+    int lseg, nseg;                      // K segmentation: close a segment after a weight block once it holds >= lseg
+                                         // main-chain MMAs; nseg segments per tile (1 in fast mode)
     int par_py[4], par_px[4], ntap[4], ngrp[4], stage_bytes[4], sbo_a[4];
     int tapoff16[4][16];                 // smem offset (16-byte units) of each tap's shifted view inside the plane
     int tapidx[4][16];                   // original filter tap index r*ks+s (weight packing)
@@ -74,6 +75,7 @@ struct alignas(64) Prob {
 constexpr int kMaxProb = 6;
 struct ArgsN {
     int nprob, total_tiles, na_stages, a_slot_bytes, nb_stages, b_slot_bytes;
+    int variant, pad_;                   // bring-up knock-outs (DANET_TC_VARIANT): 1 no stores, 2 no residual/bias loads, 4 no MMAs
     long long* prof;
     Prob p[kMaxProb];
 };
@@ -94,15 +96,23 @@ static bool make_prob(const danet_conv_desc* d, int S_req, Prob* g) {
     g->Wo = (d->W + 2 * d->pad - d->ksize) / d->stride + 1;
     if (g->Ho < 1 || g->Wo < 1) return false;
     // N tiling / accumulators
+    // exact mode: N tiles of <= 128 channels, so that the hi and lo weight rows of a tap form ONE operand of 2*NT <= 256
+    // rows (hi*[hi|lo] is one MMA) and the small terms get their own accumulator columns [NT, 2*NT)
     const int np = (d->Cout + 15) / 16 * 16;
-    g->ntn = (np + 255) / 256;
+    const int ntmax = g->exact ? 128 : 256;
+    g->ntn = (np + ntmax - 1) / ntmax;
     g->NT = ((np + g->ntn - 1) / g->ntn + 15) / 16 * 16;
-    g->nconcat = (g->exact && 2 * g->NT <= 256 && env_int("DANET_TC_NCONCAT", 1)) ? 1 : 0;
-    g->wsplit = (g->exact && !g->nconcat) ? 1 : 0;
+    g->nconcat = g->exact;
     g->ACC = g->NT * (g->nconcat ? 2 : 1);
     int S = S_req;
     if (g->Wo <= kTileW) S = 1;
+    if (g->exact && S * g->ACC > 256) S = 1;        // segmented accumulation wants two accumulator stages
     if (S * g->ACC > 512) S = 1;
+    // sub-tile pairs only pay when the image is wide enough that few pairs are half empty and there are tiles to spare
+    {
+        const long long tiles2 = (long long)d->N * ((g->Ho + kTileH - 1) / kTileH) * ((g->Wo + 2 * kTileW - 1) / (2 * kTileW)) * g->ntn;
+        if (S == 2 && tiles2 < 2 * 148) S = 1;
+    }
     g->S = S;
     g->big = S * g->ACC > 256 ? 1 : 0;
     // parity decomposition: a stride-2 convolution is the sum over the input parities (py,px) of dense
@@ -143,7 +153,7 @@ static bool make_prob(const danet_conv_desc* d, int S_req, Prob* g) {
         g->stage_bytes[a] = Hb * Wb * swb;
         g->sbo_a[a] = Wb * swb;
         g->ngrp[a] = (g->ntap[a] + tg - 1) / tg;
-        g->bpc += g->ngrp[a] * (g->wsplit ? 2 : 1);
+        g->bpc += g->ngrp[a];
         for (int k = 0; k < 16; ++k) { g->tapoff16[a][k] = 0; g->tapidx[a][k] = 0; }
         for (int k = 0; k < g->ntap[a]; ++k) {
             const int ti = k / tc_[a], tj = k % tc_[a];
@@ -152,6 +162,29 @@ static bool make_prob(const danet_conv_desc* d, int S_req, Prob* g) {
         }
     }
     g->nblk = g->nchunks * g->bpc;
+    // K segmentation (exact mode): the tensor core accumulates with truncation, which biases long chains; a tile's K loop
+    // is cut after a weight block once >= lseg MMAs went into the main accumulator, and the epilogue sums the segments
+    // in fp32 round-to-nearest.  Needs all units of a warp in registers (<= 4) and two accumulator stages.
+    g->lseg = 1 << 30; g->nseg = 1;
+    {
+        const int gph0 = (g->NT / 16 + 1) / 2;
+        if (g->exact && !g->big && g->S * gph0 <= 4) {
+            g->lseg = env_int("DANET_TC_LSEG", 12);
+            int cnt = 0, nseg = 0;
+            for (int c = 0; c < g->nchunks; ++c) {
+                const int kreal = (d->Cin - c * g->KCH + 15) / 16, kmma = g->KCH / 16;
+                const int kv = kreal < kmma ? kreal : kmma;
+                for (int a = 0; a < g->npa; ++a)
+                    for (int t = 0; t < g->ngrp[a]; ++t) {
+                        const int ntk = g->ntap[a] - t * g->TG < g->TG ? g->ntap[a] - t * g->TG : g->TG;
+                        cnt += ntk * kv;
+                        const bool last = c == g->nchunks - 1 && a == g->npa - 1 && t == g->ngrp[a] - 1;
+                        if (last || cnt >= g->lseg) { ++nseg; cnt = 0; }
+                    }
+            }
+            g->nseg = nseg;
+        }
+    }
     g->blocks_per_set = (long long)g->ntn * g->nblk;
     g->tiles_w = (g->Wo + kTileW * S - 1) / (kTileW * S); g->tiles_h = (g->Ho + kTileH - 1) / kTileH;
     const long long tiles = (long long)d->N * g->tiles_h * g->tiles_w * g->ntn;
@@ -254,6 +287,17 @@ __device__ __forceinline__ void tc_ld16x256_x2_nowait(uint32_t taddr, float* v) 
         : "r"(taddr) : "memory");
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+// 32 lanes x 32 bits, 16 columns: thread i of the warp receives TMEM lane (base lane + i), columns 0..15
+__device__ __forceinline__ void tc_ld32x32_x16_nowait(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // K-major swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1).
@@ -365,38 +409,31 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
             while (tile >= a.p[pi].tile_base + a.p[pi].tile_count) ++pi;
             const Prob& P = a.p[pi];
-            int cs = 0;
-            if (P.big) {
-                mbar_wait(bar_acc_empty, (eph & 1u) ^ 1u); mbar_wait(bar_acc_empty + 8, ((eph >> 1) & 1u) ^ 1u);
-                eph ^= 3u;
-            } else {
-                cs = tog; tog ^= 1;
-                mbar_wait(bar_acc_empty + 8 * cs, ((eph >> cs) & 1u) ^ 1u);
-                eph ^= 1u << cs;
-            }
-            tc_fence_after();
-            const uint32_t d_base = tmem_base + cs * 256;
+            const TileCoord tc = decode_tile(P, tile - P.tile_base);
+            const int exact = P.exact, big = P.big, lseg = P.lseg, nchunks = P.nchunks, npa = P.npa, TG = P.TG, SWB = P.SWB;
+            // the second sub-tile of the last tile column may lie wholly outside the image: its MMAs are skipped
+            const bool S2 = P.S == 2 && (tc.tw * 2 + 1) * kTileW < P.Wo;
+            const uint32_t ACC = (uint32_t)P.ACC, NT = (uint32_t)P.NT;
             // kind::f16, A/B = F16 (format 0), D = F32, both K-major, N>>3 at bit 17, M>>4 at bit 24
-            const uint32_t idesc1 = (1u << 4) | ((uint32_t)(P.NT >> 3) << 17) | ((128u >> 4) << 24);
-            const uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * P.NT) >> 3) << 17) | ((128u >> 4) << 24);
-            const uint32_t ltype = P.SWB == 128 ? 2u : (P.SWB == 64 ? 4u : 6u);
-            const uint64_t bd0 = make_desc(0, 8 * P.SWB, ltype);
-            const int kmma = P.KCH / 16;                         // K = 16 halves (32 bytes) per MMA
+            const uint32_t idesc1 = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * NT) >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t ltype = SWB == 128 ? 2u : (SWB == 64 ? 4u : 6u);
+            const uint64_t bd0 = make_desc(0, 8 * SWB, ltype);
+            const int kmma = P.KCH / 16;                          // K = 16 halves (32 bytes) per MMA
             const uint32_t tap16 = P.tap_bytes >> 4;
-            const int mode = !P.exact ? 0 : (P.nconcat ? 1 : 2);
-            const bool S2 = P.S == 2;
-            const uint32_t ACC = (uint32_t)P.ACC;
-            const uint32_t sub16 = (uint32_t)(kTileW * P.SWB) >> 4;
-            uint32_t acc = 0;
-            for (int c = 0; c < P.nchunks; ++c) {
+            const uint32_t sub16 = (uint32_t)(kTileW * SWB) >> 4;
+            bool need_acc = true;                                 // next MMA opens a K segment: take an accumulator stage
+            uint32_t acc = 0, d_base = 0;
+            int cs = 0, seg_cnt = 0;
+            for (int c = 0; c < nchunks; ++c) {
                 const int kreal = (P.Cin - c * P.KCH + 15) >> 4;
-                const int kv = kreal < kmma ? kreal : kmma;      // K steps wholly beyond Cin are not issued
-                for (int slot = 0; slot < P.npa; ++slot) {
+                const int kv = kreal < kmma ? kreal : kmma;       // K steps wholly beyond Cin are not issued
+                for (int slot = 0; slot < npa; ++slot) {
                     const int as_hi = as;
                     mbar_wait(bar_a_full + 8 * as, (aph >> as) & 1u);
                     aph ^= 1u << as; if (++as == a.na_stages) as = 0;
                     int as_lo = as_hi;
-                    if (P.exact) {
+                    if (exact) {
                         as_lo = as;
                         mbar_wait(bar_a_full + 8 * as, (aph >> as) & 1u);
                         aph ^= 1u << as; if (++as == a.na_stages) as = 0;
@@ -405,31 +442,42 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
                     const uint64_t ad0 = make_desc(0, (uint32_t)P.sbo_a[slot], ltype);
                     const uint64_t ad_hi = ad0 + ((sA + as_hi * a.a_slot_bytes) >> 4);
                     const uint64_t ad_lo = ad0 + ((sA + as_lo * a.a_slot_bytes) >> 4);
-                    for (int tg = 0; tg < P.ngrp[slot]; ++tg) {
-                        const int k0 = tg * P.TG;
-                        const int ntk = min(P.TG, P.ntap[slot] - k0);
+                    const int ngrp = P.ngrp[slot], ntap = P.ntap[slot];
+                    for (int tg = 0; tg < ngrp; ++tg) {
+                        const int k0 = tg * TG;
+                        const int ntk = min(TG, ntap - k0);
+                        if (need_acc) {
+                            if (big) {
+                                mbar_wait(bar_acc_empty, (eph & 1u) ^ 1u); mbar_wait(bar_acc_empty + 8, ((eph >> 1) & 1u) ^ 1u);
+                                eph ^= 3u; cs = 0;
+                            } else {
+                                cs = tog; tog ^= 1;
+                                mbar_wait(bar_acc_empty + 8 * cs, ((eph >> cs) & 1u) ^ 1u);
+                                eph ^= 1u << cs;
+                            }
+                            tc_fence_after();
+                            d_base = tmem_base + cs * 256;
+                            acc = 0; need_acc = false; seg_cnt = 0;
+                        }
                         mbar_wait(bar_b_full + 8 * bs, (bph >> bs) & 1u);
                         tc_fence_after();
                         const uint64_t bd = bd0 + ((sB + bs * a.b_slot_bytes) >> 4);
                         if (elect_one()) {
-                            for (int tt = 0; tt < ntk; ++tt) {
+                            for (int tt = 0; tt < ((a.variant & 4) ? 0 : ntk); ++tt) {
                                 const uint32_t toff = (uint32_t)P.tapoff16[slot][k0 + tt];
                                 for (int kk = 0; kk < kv; ++kk) {
                                     const uint64_t bdk = bd + tt * tap16 + 2 * kk;
                                     const uint64_t adh = ad_hi + toff + 2 * kk, adl = ad_lo + toff + 2 * kk;
-                                    if (mode == 0) {
+                                    if (!exact) {
                                         tc_mma_f16(d_base, adh, bdk, idesc1, acc);
                                         if (S2) tc_mma_f16(d_base + ACC, adh + sub16, bdk, idesc1, acc);
-                                    } else if (mode == 1) {                       // nconcat: hi * [hi | lo], then lo * hi
+                                    } else {
+                                        // hi * [hi | lo]: main chain in columns [0, NT), small terms in [NT, 2 NT);
+                                        // lo * hi joins the small terms
                                         tc_mma_f16(d_base, adh, bdk, idesc2, acc);
                                         if (S2) tc_mma_f16(d_base + ACC, adh + sub16, bdk, idesc2, acc);
-                                        tc_mma_f16(d_base, adl, bdk, idesc1, 1u);
-                                        if (S2) tc_mma_f16(d_base + ACC, adl + sub16, bdk, idesc1, 1u);
-                                    } else {                                      // hi * hi, lo * hi (hi * lo from the next block)
-                                        tc_mma_f16(d_base, adh, bdk, idesc1, acc);
-                                        if (S2) tc_mma_f16(d_base + ACC, adh + sub16, bdk, idesc1, acc);
-                                        tc_mma_f16(d_base, adl, bdk, idesc1, 1u);
-                                        if (S2) tc_mma_f16(d_base + ACC, adl + sub16, bdk, idesc1, 1u);
+                                        tc_mma_f16(d_base + NT, adl, bdk, idesc1, 1u);
+                                        if (S2) tc_mma_f16(d_base + ACC + NT, adl + sub16, bdk, idesc1, 1u);
                                     }
                                     acc = 1;
                                 }
@@ -439,192 +487,173 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
                         __syncwarp();
                         acc = 1;
                         bph ^= 1u << bs; if (++bs == a.nb_stages) bs = 0;
-                        if (P.wsplit) {
-                            // the lo weight rows of the same taps: hi * lo
-                            mbar_wait(bar_b_full + 8 * bs, (bph >> bs) & 1u);
-                            tc_fence_after();
-                            const uint64_t bl = bd0 + ((sB + bs * a.b_slot_bytes) >> 4);
-                            if (elect_one()) {
-                                for (int tt = 0; tt < ntk; ++tt) {
-                                    const uint32_t toff = (uint32_t)P.tapoff16[slot][k0 + tt];
-                                    for (int kk = 0; kk < kv; ++kk) {
-                                        tc_mma_f16(d_base, ad_hi + toff + 2 * kk, bl + tt * tap16 + 2 * kk, idesc1, 1u);
-                                        if (S2) tc_mma_f16(d_base + ACC, ad_hi + toff + sub16 + 2 * kk, bl + tt * tap16 + 2 * kk, idesc1, 1u);
-                                    }
-                                }
-                                tc_commit(bar_b_empty + 8 * bs);
-                            }
+                        seg_cnt += ntk * kv;
+                        const bool last = c == nchunks - 1 && slot == npa - 1 && tg == ngrp - 1;
+                        if (last || seg_cnt >= lseg) {            // close the K segment: hand the accumulator to the epilogue
+                            if (elect_one()) tc_commit(bar_acc_full + 8 * cs);
                             __syncwarp();
-                            bph ^= 1u << bs; if (++bs == a.nb_stages) bs = 0;
+                            need_acc = true;
                         }
                     }
                     if (elect_one()) {
                         tc_commit(bar_a_empty + 8 * as_hi);
-                        if (P.exact) tc_commit(bar_a_empty + 8 * as_lo);
+                        if (exact) tc_commit(bar_a_empty + 8 * as_lo);
                     }
                     __syncwarp();
                 }
             }
-            if (elect_one()) tc_commit(bar_acc_full + 8 * cs);
-            __syncwarp();
         }
     } else {
-        // ================= epilogue: TMEM -> bias/residual/ReLU -> global =================
-        // Quad mapping (tcgen05.ld 16x256b): a thread owns tile column wwq = lane/4 of the four tile rows 4q..4q+3 and,
-        // per 16-column group, channels 2*(lane%4)+{0,1} and +8: the four lanes of a quad read/write one whole 32-byte
-        // sector; a warp instruction touches 8 lines instead of 32.  Each of the two warps of a TMEM lane quarter takes
-        // every other 16-column group.  Residual + bias operands of up to three units ahead are held in registers and
-        // the first three are requested BEFORE the accumulator wait.
+        // ================= epilogue: TMEM -> (+ bias, residual) -> ReLU -> global =================
+        // Row-per-thread mapping (tcgen05.ld 32x32b.x16): lane i of a warp owns TMEM lane 32q+i = output pixel
+        // (tile row 4q + i/8, column i%8) and receives 16 consecutive output channels per load: every global access
+        // is a 16-byte vector of one pixel.  A "unit" = (sub-tile, 16-column group); the two warps of a TMEM lane
+        // quarter take alternate groups.  Per batch of <= 4 units the register accumulators are INITIALISED with
+        // bias + residual (all their global loads are issued before the accumulator wait, one latency exposure per
+        // tile, under the MMAs of the same tile), then every K segment of the tile is added from TMEM in fp32
+        // (round-to-nearest: the tensor core's own accumulation truncates, so long K chains are cut into segments),
+        // then ReLU, split into hi/lo fp16 planes and stored.
         const int q = warp & 3;                                  // TMEM lane quarter this warp may access
         const int half = warp >> 2;                              // 0/1: which 16-column groups this warp owns
-        const int wwq = lane >> 2, cq = 2 * (lane & 3);
-        const bool odd = lane & 1;
+        const int prow = 4 * q + (lane >> 3), pcol = lane & 7;    // this thread's pixel inside the sub-tile
         uint32_t fph = 0; int tog = 0;
         int pi = 0;
+        const bool do_store = !(a.variant & 1);
         pdl_wait();                                              // residual reads / output writes
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
             while (tile >= a.p[pi].tile_base + a.p[pi].tile_count) ++pi;
             const Prob& P = a.p[pi];
             const TileCoord tc = decode_tile(P, tile - P.tile_base);
-            int cs = 0;
-            if (!P.big) { cs = tog; tog ^= 1; }
-            const int ngroups = P.NT / 16;
+            const int NT = P.NT, ACC = P.ACC, S = P.S, nseg = P.nseg, nconcat = P.nconcat, relu = P.relu, big = P.big;
+            const int Cout = P.Cout, Wo = P.Wo, Ho = P.Ho;
+            const float* __restrict__ bias = P.bias;
+            const float* __restrict__ res_f = (a.variant & 2) ? nullptr : P.res_f;
+            const __half* __restrict__ res_hi = (a.variant & 2) ? nullptr : P.res_hi;
+            const __half* __restrict__ res_lo = P.res_lo;
+            float* __restrict__ y_f = P.y_f; __half* __restrict__ y_hi = P.y_hi; __half* __restrict__ y_lo = P.y_lo;
+            const int ngroups = NT >> 4;
             const int gph = (ngroups - half + 1) >> 1;            // groups this warp owns per sub-tile
-            const int nunits = P.S * gph;
-            const int oh0 = tc.th * kTileH + 4 * q;
-            const uint32_t rowstep = (uint32_t)(P.Wo * P.Cout);
-            const int cw = P.Cout - tc.nt * P.NT;                 // channels of this N tile that exist (multiple of 8)
-            const int boff = (tc.img - mdiv(tc.img, P.m_ws) * P.wsets) * P.Cout + tc.nt * P.NT + cq;
-            const bool has_res = P.res_f != nullptr || P.res_hi != nullptr;
-            // unit u -> (sub-tile s, column group grp); element offset of this thread's first pixel / channel
-            auto unit_s = [&](int u) { return u / gph; };
-            auto unit_grp = [&](int u) { return half + 2 * (u - (u / gph) * gph); };
-            auto pix_of = [&](int s) {
-                const int ow = (tc.tw * P.S + s) * kTileW + wwq;
-                return ((uint32_t)(tc.img * P.Ho + oh0) * P.Wo + ow) * P.Cout + tc.nt * P.NT + cq;
-            };
-            auto nrows_of = [&](int s) {
-                const int ow = (tc.tw * P.S + s) * kTileW + wwq;
-                return ow < P.Wo ? min(4, P.Ho - oh0) : 0;        // valid tile rows of this thread (<= 0: none)
-            };
-            // rv[2k+i] = bias + residual of row k, channel block i (two channels)
-            auto fetch = [&](int u, float2* rv) {
-                if (u >= nunits) return;
-                const int s = unit_s(u), grp = unit_grp(u);
-                const uint32_t pix0 = pix_of(s);
-                const int nrows = nrows_of(s);
+            const int nunits = S * gph;
+            const int cw = Cout - tc.nt * NT;                     // channels of this N tile that exist (multiple of 8)
+            const int oh = tc.th * kTileH + prow;
+            const int boff = (tc.img - mdiv(tc.img, P.m_ws) * P.wsets) * Cout + tc.nt * NT;
+            const uint32_t rowbase = (uint32_t)(tc.img * Ho + oh) * Wo;
+            const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+            int cs_first = 0;
+            for (int u0 = 0; u0 < (nunits > 0 ? nunits : 1); u0 += 4) {
+                float acc[4][16];
+                uint32_t eoff[4]; int cou[4]; bool okp[4];
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const int co = grp * 16 + 8 * i;
-                    float2 bb = make_float2(0.f, 0.f);
-                    if (P.bias && co < cw) bb = __ldg(reinterpret_cast<const float2*>(P.bias + boff + co));
+                for (int uu = 0; uu < 4; ++uu) {
+                    const int u = u0 + uu;
+                    const int s = u / gph, grp = half + 2 * (u - s * gph);
+                    const int ow = (tc.tw * S + s) * kTileW + pcol;
+                    cou[uu] = grp * 16;
+                    okp[uu] = u < nunits && oh < Ho && ow < Wo;
+                    eoff[uu] = (rowbase + ow) * Cout + tc.nt * NT + grp * 16;
+                    // accumulator <- bias (+ residual)
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        float2 r = bb;
-                        if (has_res && k < nrows && co < cw) {
-                            const uint32_t e = pix0 + k * rowstep + co;
-                            if (P.res_f) {
-                                const float2 t = __ldg(reinterpret_cast<const float2*>(P.res_f + e));
-                                r.x += t.x; r.y += t.y;
-                            } else {
-                                const float2 t = __half22float2(__ldg(reinterpret_cast<const __half2*>(P.res_hi + e)));
-                                r.x += t.x; r.y += t.y;
-                                if (P.res_lo) {
-                                    const float2 t2 = __half22float2(__ldg(reinterpret_cast<const __half2*>(P.res_lo + e)));
-                                    r.x += t2.x; r.y += t2.y;
+                    for (int h = 0; h < 2; ++h) {
+                        const int co = grp * 16 + 8 * h;
+                        const bool ch_ok = u < nunits && co < cw;
+                        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+                        if (bias && ch_ok) { b0 = __ldg(reinterpret_cast<const float4*>(bias + boff + co)); b1 = __ldg(reinterpret_cast<const float4*>(bias + boff + co + 4)); }
+                        float* ac = &acc[uu][8 * h];
+                        ac[0] = b0.x; ac[1] = b0.y; ac[2] = b0.z; ac[3] = b0.w; ac[4] = b1.x; ac[5] = b1.y; ac[6] = b1.z; ac[7] = b1.w;
+                        if (okp[uu] && ch_ok) {
+                            if (res_f) {
+                                const float4 r0 = __ldg(reinterpret_cast<const float4*>(res_f + eoff[uu] + 8 * h));
+                                const float4 r1 = __ldg(reinterpret_cast<const float4*>(res_f + eoff[uu] + 8 * h + 4));
+                                ac[0] += r0.x; ac[1] += r0.y; ac[2] += r0.z; ac[3] += r0.w; ac[4] += r1.x; ac[5] += r1.y; ac[6] += r1.z; ac[7] += r1.w;
+                            } else if (res_hi) {
+                                const uint4 rh = __ldg(reinterpret_cast<const uint4*>(res_hi + eoff[uu] + 8 * h));
+                                float2 t;
+                                t = h2_to_f2(rh.x); ac[0] += t.x; ac[1] += t.y; t = h2_to_f2(rh.y); ac[2] += t.x; ac[3] += t.y;
+                                t = h2_to_f2(rh.z); ac[4] += t.x; ac[5] += t.y; t = h2_to_f2(rh.w); ac[6] += t.x; ac[7] += t.y;
+                                if (res_lo) {
+                                    const uint4 rl = __ldg(reinterpret_cast<const uint4*>(res_lo + eoff[uu] + 8 * h));
+                                    t = h2_to_f2(rl.x); ac[0] += t.x; ac[1] += t.y; t = h2_to_f2(rl.y); ac[2] += t.x; ac[3] += t.y;
+                                    t = h2_to_f2(rl.z); ac[4] += t.x; ac[5] += t.y; t = h2_to_f2(rl.w); ac[6] += t.x; ac[7] += t.y;
                                 }
                             }
                         }
-                        rv[2 * k + i] = r;
                     }
                 }
-            };
-            auto finish = [&](int u, const float2* rv) {
-                const int s = unit_s(u), grp = unit_grp(u);
-                const uint32_t pix0 = pix_of(s);
-                const int nrows = nrows_of(s);
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cs * 256 + s * P.ACC + grp * 16;
-                float va[8], vb[8];
-                tc_ld16x256_x2_nowait(taddr, va);
-                tc_ld16x256_x2_nowait(taddr + (16u << 16), vb);
-                if (P.nconcat) {
-                    float wa[8], wb[8];
-                    tc_ld16x256_x2_nowait(taddr + P.NT, wa);
-                    tc_ld16x256_x2_nowait(taddr + (16u << 16) + P.NT, wb);
-                    tc_wait_ld();
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) { va[j] += wa[j]; vb[j] += wb[j]; }
-                } else {
-                    tc_wait_ld();
-                }
-                float2 o[2][4];
-#pragma unroll
-                for (int i = 0; i < 2; ++i)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const float* v = (k < 2 ? va : vb) + 4 * i + 2 * (k & 1);
-                        float2 t = make_float2(v[0] + rv[2 * k + i].x, v[1] + rv[2 * k + i].y);
-                        if (P.relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); }
-                        o[i][k] = t;
+                // add every K segment of the tile from TMEM (a multi-batch tile has a single segment)
+                for (int seg = 0; seg < nseg; ++seg) {
+                    int cs = cs_first;
+                    if (u0 == 0) {
+                        cs = 0;
+                        if (!big) { cs = tog; tog ^= 1; }
+                        mbar_wait(bar_acc_full + 8 * cs, (fph >> cs) & 1u);
+                        fph ^= 1u << cs;
+                        tc_fence_after();
+                        cs_first = cs;
                     }
-                if (P.y_f) {
+                    // TMEM -> registers two units at a time (32 temporaries), main range then small-term range
+                    const int nrange = nconcat ? 2 : 1;
+                    for (int rg = 0; rg < nrange; ++rg) {
 #pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const int co = grp * 16 + 8 * i;
-                        if (co >= cw) continue;
+                        for (int up = 0; up < 4; up += 2) {
+                            if (u0 + up >= nunits) break;
+                            float v[2][16];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            if (k < nrows) *reinterpret_cast<float2*>(P.y_f + pix0 + k * rowstep + co) = o[i][k];
-                    }
-                }
-                if (P.y_hi) {
-                    // fp16 planes: the two 8-column blocks of the group are paired up inside the quad (one shuffle with the
-                    // neighbour lane per row): even lanes store 4 halves of block 0, odd lanes 4 halves of block 1 -- 8-byte
-                    // stores.  Cout % 8 == 0, so a block is valid or not for the whole quad (no divergence at the shuffle).
-                    const int col = grp * 16 + (odd ? 8 : 0);               // first column of the block this lane stores
-                    const bool blk_ok = col < cw;
-                    const uint32_t e0 = (pix0 - cq) + col + (odd ? cq - 2 : cq);
-                    uint32_t ph[2][4], pl[2][4];
+                            for (int w2 = 0; w2 < 2; ++w2) {
+                                const int u = u0 + up + w2;
+                                if (u < nunits) {
+                                    const int s = u / gph, grp = half + 2 * (u - s * gph);
+                                    tc_ld32x32_x16_nowait(tlane + cs * 256 + s * ACC + rg * NT + grp * 16, v[w2]);
+                                }
+                            }
+                            tc_wait_ld();
 #pragma unroll
-                    for (int i = 0; i < 2; ++i)
+                            for (int w2 = 0; w2 < 2; ++w2)
+                                if (u0 + up + w2 < nunits) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint32_t h = pack_h2_rn(o[i][k].x, o[i][k].y);
-                            ph[i][k] = h;
-                            const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h));
-                            pl[i][k] = pack_h2_rn(o[i][k].x - hf.x, o[i][k].y - hf.y);
-                        }
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t recv = __shfl_xor_sync(0xffffffffu, odd ? ph[0][k] : ph[1][k], 1);
-                        const uint32_t lo = odd ? recv : ph[0][k], hi = odd ? ph[1][k] : recv;
-                        if (blk_ok && k < nrows) *reinterpret_cast<uint2*>(P.y_hi + e0 + k * rowstep) = make_uint2(lo, hi);
-                    }
-                    if (P.y_lo) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint32_t recv = __shfl_xor_sync(0xffffffffu, odd ? pl[0][k] : pl[1][k], 1);
-                            const uint32_t lo = odd ? recv : pl[0][k], hi = odd ? pl[1][k] : recv;
-                            if (blk_ok && k < nrows) *reinterpret_cast<uint2*>(P.y_lo + e0 + k * rowstep) = make_uint2(lo, hi);
+                                    for (int j = 0; j < 16; ++j) acc[up + w2][j] += v[w2][j];
+                                }
                         }
                     }
+                    if (u0 + 4 >= nunits) {                      // last batch: the accumulator stage is free again
+                        tc_fence_before();
+                        if (big) { mbar_arrive(bar_acc_empty); mbar_arrive(bar_acc_empty + 8); }
+                        else mbar_arrive(bar_acc_empty + 8 * cs);
+                    }
                 }
-            };
-            float2 r0[8], r1[8], r2[8];
+                // ReLU, split, store
 #pragma unroll
-            for (int i = 0; i < 8; ++i) r0[i] = r1[i] = r2[i] = make_float2(0.f, 0.f);
-            fetch(0, r0); fetch(1, r1); fetch(2, r2);
-            mbar_wait(bar_acc_full + 8 * cs, (fph >> cs) & 1u);
-            fph ^= 1u << cs;
-            tc_fence_after();
-            for (int u = 0; u < nunits; u += 3) {
-                finish(u, r0); fetch(u + 3, r0);
-                if (u + 1 < nunits) { finish(u + 1, r1); fetch(u + 4, r1); }
-                if (u + 2 < nunits) { finish(u + 2, r2); fetch(u + 5, r2); }
+                for (int uu = 0; uu < 4; ++uu) {
+                    if (!(okp[uu] && do_store)) continue;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (cou[uu] + 8 * h >= cw) continue;
+                        float* ac = &acc[uu][8 * h];
+                        if (relu) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) ac[j] = fmaxf(ac[j], 0.f);
+                        }
+                        const uint32_t e = eoff[uu] + 8 * h;
+                        if (y_f) {
+                            *reinterpret_cast<float4*>(y_f + e) = make_float4(ac[0], ac[1], ac[2], ac[3]);
+                            *reinterpret_cast<float4*>(y_f + e + 4) = make_float4(ac[4], ac[5], ac[6], ac[7]);
+                        }
+                        if (y_hi) {
+                            uint4 hv;
+                            hv.x = pack_h2_rn(ac[0], ac[1]); hv.y = pack_h2_rn(ac[2], ac[3]);
+                            hv.z = pack_h2_rn(ac[4], ac[5]); hv.w = pack_h2_rn(ac[6], ac[7]);
+                            *reinterpret_cast<uint4*>(y_hi + e) = hv;
+                            if (y_lo) {
+                                float2 t; uint4 lv;
+                                t = h2_to_f2(hv.x); lv.x = pack_h2_rn(ac[0] - t.x, ac[1] - t.y);
+                                t = h2_to_f2(hv.y); lv.y = pack_h2_rn(ac[2] - t.x, ac[3] - t.y);
+                                t = h2_to_f2(hv.z); lv.z = pack_h2_rn(ac[4] - t.x, ac[5] - t.y);
+                                t = h2_to_f2(hv.w); lv.w = pack_h2_rn(ac[6] - t.x, ac[7] - t.y);
+                                *reinterpret_cast<uint4*>(y_lo + e) = lv;
+                            }
+                        }
+                    }
+                }
             }
-            tc_fence_before();
-            if (P.big) { mbar_arrive(bar_acc_empty); mbar_arrive(bar_acc_empty + 8); }
-            else mbar_arrive(bar_acc_empty + 8 * cs);
         }
     }
     tc_fence_before();
@@ -657,9 +686,8 @@ __global__ void k_pack(const Prob g, const float* __restrict__ w, __half* __rest
         if (g.nconcat && n >= g.NT) { n -= g.NT; want_lo = 1; }
         int bi = (int)(blk % g.bpc); blk /= g.bpc;
         int slot = 0, base = 0;
-        for (;;) { const int nb = g.ngrp[slot] * (g.wsplit ? 2 : 1); if (bi < base + nb || slot + 1 >= g.npa) break; base += nb; ++slot; }
-        int tgi = bi - base;
-        if (g.wsplit) { want_lo = tgi & 1; tgi >>= 1; }
+        for (;;) { const int nb = g.ngrp[slot]; if (bi < base + nb || slot + 1 >= g.npa) break; base += nb; ++slot; }
+        const int tgi = bi - base;
         const int c = (int)(blk % g.nchunks); blk /= g.nchunks;
         const int nt = (int)(blk % g.ntn);
         const int ws = (int)(blk / g.ntn);
@@ -756,12 +784,30 @@ int conv_tc_group_launch(int n, const danet_conv_problem* probs, cudaStream_t st
         DANET_CHECK(worst >= 0 && attempt < 2 * kMaxProb, "danet_conv_tc_group: shared-memory plan does not fit");
         S_req[worst] = 1;
     }
+    // tiles are dealt round-robin over the persistent CTAs in problem order: the problems with the most expensive
+    // tiles go first, so that the long tiles start early and the cheap ones fill the tail
+    int order[kMaxProb];
+    double tcost[kMaxProb];
+    for (int i = 0; i < n; ++i) {
+        const Prob& P = a.p[i];
+        int taps = 0;
+        for (int s2 = 0; s2 < P.npa; ++s2) taps += P.ntap[s2];
+        tcost[i] = (double)P.S * taps * ((P.Cin + 15) / 16) * (P.exact ? 2.0 : 1.0) * (128 + P.NT * (P.exact ? 1.5 : 1.0));
+        order[i] = i;
+    }
+    for (int i = 1; i < n; ++i)
+        for (int j = i; j > 0 && tcost[order[j]] > tcost[order[j - 1]]; --j) { const int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t; }
+    {
+        ArgsN* tmp = new ArgsN(a);
+        for (int i = 0; i < n; ++i) a.p[i] = tmp->p[order[i]];
+        delete tmp;
+    }
     int base = 0;
     for (int i = 0; i < n; ++i) {
         Prob& P = a.p[i];
-        const danet_conv_problem& q = probs[i];
-        DANET_CHECK(q.x.hi && q.w_packed && (q.y.hi || q.y.f32), "danet_conv_tc_group: problem %d: null x.hi / weights / output", i);
-        DANET_CHECK(!P.exact || q.x.lo, "danet_conv_tc_group: problem %d: exact mode needs the x.lo plane", i);
+        const danet_conv_problem& q = probs[order[i]];
+        DANET_CHECK(q.x.hi && q.w_packed && (q.y.hi || q.y.f32), "danet_conv_tc_group: problem %d: null x.hi / weights / output", order[i]);
+        DANET_CHECK(!P.exact || q.x.lo, "danet_conv_tc_group: problem %d: exact mode needs the x.lo plane", order[i]);
         P.wpk = (const uint8_t*)q.w_packed; P.bias = q.bias;
         P.res_f = q.res.f32; P.res_hi = (const __half*)q.res.hi; P.res_lo = (const __half*)q.res.lo;
         if (P.res_f) { P.res_hi = nullptr; P.res_lo = nullptr; }
@@ -774,6 +820,7 @@ int conv_tc_group_launch(int n, const danet_conv_problem* probs, cudaStream_t st
     }
     a.total_tiles = base;
     a.prof = nullptr;
+    a.variant = env_int("DANET_TC_VARIANT", 0);
     int dev = 0;
     DANET_CUDA(cudaGetDevice(&dev));
     DANET_CHECK(dev >= 0 && dev < 64, "conv_tc: device ordinal %d out of range", dev);

@@ -3,8 +3,15 @@
 // and the vertex-regressed joints (extra 9, H36M 17, 21 picked vertices) -> 49-joint output.
 //
 // Replaces models/smpl.py:15-46 + smplx.lbs (third-party, see oracle/lbs.py) and
-// utils/geometry.py:9-91.  fp32 SIMT: the products are 3x3 / 3x4 / 207-long dot products per
-// vertex coordinate -- no tensor-core shape.  Three launches per forward:
+// utils/geometry.py:9-91.  Two routes:
+//  * small batches (B < kGemmMinB): everything fp32 SIMT in one fused kernel (below);
+//  * large batches: the blend-shape + pose-corrective contraction  v_posed[B, 20670] = template +
+//    [pose_feature | betas][B, 224] x [posedirs ; shapedirs][224, 20670]  is a genuine GEMM (4.5 MMAC per body,
+//    88 % of the layer's arithmetic) and runs on the tcgen05 engine of conv_tc.cu as a 1x1 "convolution" whose
+//    pixels are the bodies (exact mode: split-fp16 operands, 3 MMAs, fp32 accumulation -> fp32-grade), in chunks
+//    of kGemmChunk bodies so that the fp32 v_posed chunk (85 MB) stays in the 126 MB L2 until the skinning
+//    kernel (the same k_smpl_verts, phase 1 replaced by a coalesced load) has consumed it.
+// Fused SIMT route, three launches per forward:
 //   k_smpl_pose    one thread per body: rotations, rest joints (linear in beta, precomputed
 //                  J_template + J_shapedirs*beta), chain -> A[B,24,3x4], pose_feature[B,208]
 //   k_smpl_verts   grid (54 vertex tiles, B/NB body chunks), 128 threads:
@@ -15,6 +22,7 @@
 //   k_smpl_joints  one CTA per body: reduce partials in fixed tile order (deterministic), pick
 //                  vertices, apply joint_map.
 #include "common.cuh"
+#include <string.h>
 
 namespace danet {
 
@@ -23,6 +31,9 @@ constexpr int kTileV = 128;             // vertices per CTA tile
 constexpr int kTileC = kTileV * 3;      // coordinates per CTA tile
 constexpr int kPF = 208;                // padded pose-feature length (207 -> 208)
 constexpr int kMaxBetas = 16;
+constexpr int kGF = 224;                // GEMM route: feature row = 207 pose features | 0 | betas (<= 16) at 208..
+constexpr int kGemmMinB = 512;          // batches at least this large take the tensor-core GEMM route
+constexpr int kGemmChunk = 1024;        // bodies per GEMM + skinning round (fp32 v_posed chunk = 85 MB, L2-resident)
 
 struct SmplView {
     int nv, ntiles, nvpad, npad, nbetas;
@@ -47,11 +58,17 @@ struct SmplView {
     int nout; const int* joint_map;
 };
 
+int conv_tc_group_launch(int n, const danet_conv_problem* probs, cudaStream_t stream);   // conv_tc.cu
+
 }  // namespace danet
 
 struct danet_smpl {
     danet::SmplView v;
     std::vector<void*> allocs;
+    // GEMM route: packed [posedirs ; shapedirs] weights, template as bias
+    void* gemm_w = nullptr;
+    float* gemm_bias = nullptr;
+    int gemm_cout = 0;
 };
 
 namespace danet {
@@ -166,7 +183,7 @@ __global__ void k_mpjpe(int B, const float* __restrict__ j17, const float* __res
 __global__ void k_smpl_pose(int B, int pose_kind, const float* __restrict__ betas,
                             const float* __restrict__ pose, SmplView m, float* __restrict__ rot_out,
                             float* __restrict__ G, float* __restrict__ A, float* __restrict__ pf,
-                            float* __restrict__ posed) {
+                            float* __restrict__ posed, __half* __restrict__ feat_hi, __half* __restrict__ feat_lo) {
     // world transforms of the kinematic chain stay in shared memory (the parent's G is read back by
     // the same thread; a global round trip cost ~1 us per joint)
     __shared__ float s_G[32][kJ * 12 + 1];
@@ -227,6 +244,19 @@ __global__ void k_smpl_pose(int B, int pose_kind, const float* __restrict__ beta
         }
     }
     pfb[207] = 0.0f;
+    if (feat_hi) {
+        // GEMM route: [pose feature (207) | 0 | betas | 0 ...] as split-fp16 planes (hi = rn(v), lo = rn(v - hi))
+        __half* fh = feat_hi + (size_t)b * kGF;
+        __half* fl = feat_lo + (size_t)b * kGF;
+        for (int k = 0; k < kGF; ++k) {
+            float v = 0.0f;
+            if (k < 207) v = pfb[k];
+            else if (k >= 208 && k - 208 < m.nbetas) v = beta[k - 208];
+            const __half h = __float2half_rn(v);
+            fh[k] = h;
+            fl[k] = __float2half_rn(v - __half2float(h));
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -236,7 +266,7 @@ template <int NB>
 __global__ void __launch_bounds__(kTileV)
 k_smpl_verts(int B, const float* __restrict__ betas, const float* __restrict__ pf,
              const float* __restrict__ A, SmplView m, float* __restrict__ verts,
-             float* __restrict__ partials) {
+             float* __restrict__ partials, const float* __restrict__ vposed, int vp_stride) {
     extern __shared__ __align__(16) float smem_lbs[];
     float (*s_pf)[kPF] = reinterpret_cast<float (*)[kPF]>(smem_lbs);
     float (*s_A)[kJ * 12] = reinterpret_cast<float (*)[kJ * 12]>(smem_lbs + NB * kPF);
@@ -244,6 +274,7 @@ k_smpl_verts(int B, const float* __restrict__ betas, const float* __restrict__ p
     float (*s_beta)[kMaxBetas] = reinterpret_cast<float (*)[kMaxBetas]>(smem_lbs + NB * (kPF + kJ * 12 + kTileC));
 
     const int tile = blockIdx.x, b0 = blockIdx.y * NB, tid = threadIdx.x;
+    if (!vposed)
     for (int i = tid; i < NB * kPF; i += kTileV) {
         const int b = i / kPF, k = i % kPF, bb = min(b0 + b, B - 1);
         s_pf[b][k] = pf[(size_t)bb * kPF + k];
@@ -260,6 +291,18 @@ k_smpl_verts(int B, const float* __restrict__ betas, const float* __restrict__ p
 
     // ---- phase 1: v_posed[n] for n = tile*384 + tid + {0,128,256}, NB bodies ----
     const size_t n0 = (size_t)tile * kTileC + tid;
+    if (vposed) {
+        // GEMM route: v_posed comes from the tensor-core contraction (row b of vposed, vp_stride floats apart)
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const int bb = min(b0 + b, B - 1);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int n = (int)n0 + j * kTileV;
+                s_v[b][tid + j * kTileV] = n < vp_stride ? __ldg(vposed + (size_t)bb * vp_stride + n) : 0.0f;
+            }
+        }
+    } else {
     float acc[3][NB];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
@@ -303,6 +346,7 @@ k_smpl_verts(int B, const float* __restrict__ betas, const float* __restrict__ p
     for (int b = 0; b < NB; ++b)
 #pragma unroll
         for (int j = 0; j < 3; ++j) s_v[b][tid + j * kTileV] = acc[j][b];
+    }
     __syncthreads();
 
     // ---- phase 2: skinning, thread = vertex ----
@@ -544,6 +588,33 @@ extern "C" int danet_smpl_create(const danet_smpl_desc* d, danet_smpl_t* out) {
     rc |= up(h, &m.row_pair_off, rpo); rc |= up(h, &m.row_pair_slot, rps);
     rc |= up(h, &m.sel, sel); rc |= up(h, &m.joint_map, jm);
     if (rc != 0) { danet_smpl_destroy(h); return -2; }
+    // GEMM route operands: W [224][Cout] = [posedirs (207 rows) ; 0 ; shapedirs^T (nbetas rows) ; 0...], bias = template,
+    // packed into the tensor-core engine's split-fp16 weight blocks (exact mode)
+    {
+        const int cout = (nv * 3 + 7) / 8 * 8;
+        std::vector<float> W((size_t)kGF * cout, 0.f), bias(cout, 0.f);
+        for (int k = 0; k < 207; ++k)
+            for (int i = 0; i < nv * 3; ++i) W[(size_t)k * cout + i] = d->posedirs[(size_t)k * nv * 3 + i];
+        for (int l = 0; l < nb; ++l)
+            for (int i = 0; i < nv * 3; ++i) W[(size_t)(208 + l) * cout + i] = d->shapedirs[(size_t)i * nb + l];
+        for (int i = 0; i < nv * 3; ++i) bias[i] = d->v_template[i];
+        danet_conv_desc cd = {1, 128, 8, kGF, cout, 1, 1, 0, 1, 0, DANET_CONV_EXACT};
+        const int64_t pbytes = danet_conv_tc_packed_bytes(&cd);
+        h->gemm_cout = 0;
+        if (pbytes > 0) {
+            float* dW = nullptr;
+            const float* dB = nullptr;
+            if (upload(&dW, W.data(), W.size()) != 0 || up(h, &dB, bias) != 0) { danet_smpl_destroy(h); return -2; }
+            void* pk = nullptr;
+            if (cudaMalloc(&pk, (size_t)pbytes) != cudaSuccess) { cudaFree(dW); danet_smpl_destroy(h); set_error("danet_smpl_create: out of memory"); return -2; }
+            h->allocs.push_back(pk);
+            const int prc = danet_conv_tc_pack(&cd, dW, pk, nullptr);
+            cudaDeviceSynchronize();
+            cudaFree(dW);
+            if (prc != 0) { danet_smpl_destroy(h); return -2; }
+            h->gemm_w = pk; h->gemm_bias = const_cast<float*>(dB); h->gemm_cout = cout;
+        }
+    }
     *out = h;
     return 0;
 }
@@ -565,6 +636,12 @@ extern "C" int64_t danet_smpl_workspace_bytes(danet_smpl_t h, int32_t B) {
     ws_off(cur, (int64_t)B * kPF * 4);              // pose feature
     ws_off(cur, (int64_t)B * kJ * 3 * 4);           // posed joints
     ws_off(cur, (int64_t)B * (h->v.npairs > 0 ? h->v.npairs : 1) * 3 * 4);  // regressor partials
+    if (B >= kGemmMinB && h->gemm_cout > 0) {
+        const int64_t Bp = align_up(B, 8);
+        ws_off(cur, Bp * kGF * 2);                  // feature plane hi
+        ws_off(cur, Bp * kGF * 2);                  // feature plane lo
+        ws_off(cur, (int64_t)(B < kGemmChunk ? Bp : kGemmChunk) * h->gemm_cout * 4);   // fp32 v_posed of one chunk
+    }
     return cur;
 }
 
@@ -588,31 +665,57 @@ extern "C" int danet_smpl_forward(danet_smpl_t h, int32_t B, const float* betas,
     float* posed = (float*)(ws + ws_off(cur, (int64_t)B * kJ * 3 * 4));
     float* partials = (float*)(ws + ws_off(cur, (int64_t)B * (m.npairs > 0 ? m.npairs : 1) * 3 * 4));
 
-    k_smpl_pose<<<cdiv(B, 32), 32, 0, stream>>>(B, pose_kind, betas, pose, m, rotmats, G, A, pf, posed);
+    const bool gemm = B >= kGemmMinB && h->gemm_cout > 0 && bodies_per_cta >= 0;
+    __half* feat_hi = nullptr; __half* feat_lo = nullptr; float* vposed = nullptr;
+    if (gemm) {
+        const int64_t Bp = align_up(B, 8);
+        feat_hi = (__half*)(ws + ws_off(cur, Bp * kGF * 2));
+        feat_lo = (__half*)(ws + ws_off(cur, Bp * kGF * 2));
+        vposed = (float*)(ws + ws_off(cur, (int64_t)(B < kGemmChunk ? Bp : kGemmChunk) * h->gemm_cout * 4));
+    }
+    k_smpl_pose<<<cdiv(B, 32), 32, 0, stream>>>(B, pose_kind, betas, pose, m, rotmats, G, A, pf, posed, feat_hi, feat_lo);
     DANET_LAUNCH_CHECK();
     int nb = bodies_per_cta;
-    if (nb <= 0) nb = B >= 2048 ? 16 : (B >= 32 ? 8 : (B >= 4 ? 4 : (B >= 2 ? 2 : 1)));
-    dim3 grid(m.ntiles, cdiv(B, nb));
+    if (nb <= 0) nb = B >= 32 ? 8 : (B >= 4 ? 4 : (B >= 2 ? 2 : 1));      // 8 is the measured optimum on B200 (tools/lbs_sweep.py)
     const size_t smem = (size_t)nb * (kPF + kJ * 12 + kTileC + kMaxBetas) * sizeof(float);
-#define DANET_LBS_LAUNCH(NBV)                                                                       \
+#define DANET_LBS_LAUNCH(NBV, Bc, off, VP)                                                          \
     do {                                                                                            \
         static unsigned long long attr_devs = 0;                                                    \
         if (first_use_on_current_device(&attr_devs) != 0) {                                         \
             DANET_CUDA(cudaFuncSetAttribute(k_smpl_verts<NBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                             (int)((size_t)NBV * (kPF + kJ * 12 + kTileC + kMaxBetas) * sizeof(float)))); \
         }                                                                                           \
-        k_smpl_verts<NBV><<<grid, kTileV, smem, stream>>>(B, betas, pf, A, m, verts, partials);     \
+        dim3 grid(m.ntiles, cdiv(Bc, NBV));                                                         \
+        k_smpl_verts<NBV><<<grid, kTileV, smem, stream>>>(Bc, betas + (size_t)(off) * m.nbetas, pf + (size_t)(off) * kPF, \
+            A + (size_t)(off) * kJ * 12, m, verts ? verts + (size_t)(off) * m.nv * 3 : nullptr,   \
+            partials + (size_t)(off) * (m.npairs > 0 ? m.npairs : 1) * 3, VP, h->gemm_cout);       \
     } while (0)
-    switch (nb) {
-        case 1:  DANET_LBS_LAUNCH(1); break;
-        case 2:  DANET_LBS_LAUNCH(2); break;
-        case 4:  DANET_LBS_LAUNCH(4); break;
-        case 8:  DANET_LBS_LAUNCH(8); break;
-        case 16: DANET_LBS_LAUNCH(16); break;
-        default: DANET_CHECK(false, "danet_smpl_forward: bodies_per_cta must be 0,1,2,4,8,16 (got %d)", nb);
+    if (gemm) {
+        // tensor-core route: per chunk, one 1x1 "convolution" over the bodies (exact mode) + the skinning phases
+        for (int off = 0; off < B; off += kGemmChunk) {
+            const int Bc = B - off < kGemmChunk ? B - off : kGemmChunk;
+            danet_conv_problem pr;
+            memset(&pr, 0, sizeof(pr));
+            pr.d.N = 1; pr.d.H = cdiv(Bc, 8); pr.d.W = 8; pr.d.Cin = kGF; pr.d.Cout = h->gemm_cout; pr.d.ksize = 1; pr.d.stride = 1;
+            pr.d.pad = 0; pr.d.wsets = 1; pr.d.relu = 0; pr.d.flags = DANET_CONV_EXACT;
+            pr.x.hi = feat_hi + (size_t)off * kGF; pr.x.lo = feat_lo + (size_t)off * kGF;
+            pr.y.f32 = vposed; pr.w_packed = h->gemm_w; pr.bias = h->gemm_bias;
+            if (conv_tc_group_launch(1, &pr, stream) != 0) return -1;
+            DANET_LBS_LAUNCH(8, Bc, off, vposed);
+            DANET_LAUNCH_CHECK();
+        }
+    } else {
+        switch (nb) {
+            case 1:  DANET_LBS_LAUNCH(1, B, 0, nullptr); break;
+            case 2:  DANET_LBS_LAUNCH(2, B, 0, nullptr); break;
+            case 4:  DANET_LBS_LAUNCH(4, B, 0, nullptr); break;
+            case 8:  DANET_LBS_LAUNCH(8, B, 0, nullptr); break;
+            case 16: DANET_LBS_LAUNCH(16, B, 0, nullptr); break;
+            default: DANET_CHECK(false, "danet_smpl_forward: bodies_per_cta must be 0,1,2,4,8,16 (got %d)", nb);
+        }
+        DANET_LAUNCH_CHECK();
     }
 #undef DANET_LBS_LAUNCH
-    DANET_LAUNCH_CHECK();
     if (joints || smpl_joints || joints_h36m) {
         const int ncat = kJ + m.nsel + m.nrows;
         k_smpl_joints<<<B, 192, ncat * 3 * sizeof(float), stream>>>(B, m, posed, verts, partials, joints,

@@ -177,13 +177,30 @@ class SMPL(nn.Module):
         self._handles[key] = h
         return h
 
-    def __del__(self):
+    def _drop_handles(self):
+        """The device-side model (danet_smpl_t) snapshots the buffers: drop it whenever they may have changed."""
         try:
             lib = _lib.load()
             for h in self._handles.values():
                 lib.danet_smpl_destroy(h)
         except Exception:
             pass
+        self._handles = {}
+
+    def __del__(self):
+        self._drop_handles()
+
+    def _apply(self, fn, *a, **k):
+        self._drop_handles()
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        self._drop_handles()
+        return super().load_state_dict(state_dict, strict=strict, **kw)
+
+    def _load_from_state_dict(self, *a, **k):
+        self._drop_handles()
+        return super()._load_from_state_dict(*a, **k)
 
     def _workspace(self, h, B, device):
         need = _lib.load().danet_smpl_workspace_bytes(h, B)
@@ -247,8 +264,12 @@ class SMPL(nn.Module):
                                               _lib.ptr(rot), _lib.ptr(ws), int(bodies_per_cta),
                                               _lib.stream_ptr()), "smpl_forward")
         if transl is not None:
-            joints = joints + transl.unsqueeze(1)
-            verts = verts + transl.unsqueeze(1)
+            # smplx adds the translation to joints and vertices; models/smpl.py:27-46 takes smpl_joints from the
+            # translated joints, and eval.py regresses the H36M joints from the translated vertices
+            t = transl.to(dev, torch.float32).unsqueeze(1)
+            joints, verts, smpl_joints = joints + t, verts + t, smpl_joints + t
+            if jh is not None:
+                jh = jh + t
         self.last_joints_h36m = jh
         self.last_rotmats = rot if rot is not None else pose
         joints_J24 = joints[:, -24:, :]

@@ -7,7 +7,19 @@ import os
 import sys
 import types
 
-REF = os.environ.get("DANET_REFERENCE", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_ref():
+    """The reference tree: $DANET_REFERENCE, else /root/reference (this container), else oracle/_ref (the
+    git-ignored copy of the reference's own network modules that oracle/make_ref.py takes along to the GPU box)."""
+    for cand in (os.environ.get("DANET_REFERENCE"), "/root/reference", os.path.join(_HERE, "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "models", "danet")):
+            return cand
+    return "/root/reference"
+
+
+REF = _find_ref()
 
 
 def available():

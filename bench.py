@@ -321,6 +321,25 @@ def run_b200_arm(args):
                 "n_conv_tc": plan.n_tc,
                 "n_conv_total": prof["n_conv"], "other_ms": prof["other_ms"]}
         lbs = lbs_bench(smpl, dev, pk)
+        parity = parity_block(net, dev, W, B) if world == 1 else None
+        extras = {}
+        if world == 1 and not args.no_extras:
+            # BASELINE config 2: single 224x224 image, HRNet-W32, batch 1 (latency)
+            n32 = danet_b200.build_synthetic_danet(width=32, seed=0, device=dev, conv_algo=args.conv, precision=args.precision,
+                                                   use_cuda_graph=not args.no_graph)
+            ms1 = time_net(n32, n32.iuv2smpl.smpl, n32.iuv_renderer, torch.randn(1, 3, 224, 224, device=dev), 30)
+            extras["latency_b1_w32"] = {"workload": "configs[1]: DaNet forward single 224x224 image, batch=1, HRNet-W32", "ms": ms1,
+                                        "images_per_s": 1e3 / ms1}
+            del n32
+            # the other precision of the tensor-core path, same workload (device-resident), with its own parity block
+            other = "fast" if plan.precision == "exact" else "exact"
+            n2 = danet_b200.build_synthetic_danet(width=W, seed=0, device=dev, conv_algo=args.conv, precision=other,
+                                                  use_cuda_graph=not args.no_graph)
+            ms2 = time_net(n2, n2.iuv2smpl.smpl, n2.iuv_renderer, dev_in[0], max(5, args.steps))
+            extras["precision_" + other] = {"value": B / (ms2 * 1e-3), "unit": "images/s", "ms_per_step": ms2,
+                                            "tensor_frac_of_sustained_peak": (FLOP_PER_IMG.get(W, 0.0) * B / (ms2 * 1e-3) / 1e12) / tc_peak,
+                                            "parity": parity_block(n2, dev, W, B)}
+            del n2
         cpu = None
         if world == 1 and not args.no_cpu:
             cpu = cpu_baseline(W, args.cpu_batch)
@@ -340,7 +359,8 @@ def run_b200_arm(args):
                 "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * 224 * 224 * 4,
                         "d2h_bytes_per_step": B * 229 * 4 + B * 3 * 56 * 56 * 4},
                 "gpu_launches": launches_per_step * args.steps,
-                "roofline": roof, "lbs": lbs, "cpu_baseline": cpu}
+                "roofline": roof, "lbs": lbs, "parity": parity, "cpu_baseline": cpu}
+        line.update(extras)
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line))
@@ -349,6 +369,69 @@ def run_b200_arm(args):
         dist.barrier()
         dist.destroy_process_group()
     return line
+
+
+def parity_block(net, dev, width, B):
+    """The benched configuration against the reference's own outputs for the same images
+    (tests/golden/net_w48_b64.npz, produced by the reference's modules -- oracle/gen_golden_net.py): para / STN
+    centre error, integer-map agreement, and the para error carried through the SMPL layer in millimetres."""
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    gp = os.path.join(ROOT, "tests", "golden", "net_w%d_b%d.npz" % (width, B))
+    if not os.path.exists(gp):
+        return None
+    g = np.load(gp)
+    gen = torch.Generator().manual_seed(100 + int(g["seed"]))
+    low = torch.randn(B, 3, 7, 7, generator=gen)
+    img = F.interpolate(low, size=224, mode="bilinear", align_corners=False) * 2 + 0.3 * torch.randn(B, 3, 224, 224, generator=gen)
+    out = net.infer_net(img.to(dev))
+    para = out["para"]
+    ref = torch.from_numpy(g["para"]).to(dev)
+    smpl = net.iuv2smpl.smpl
+
+    def verts(p):
+        R = p[:, 13:].reshape(-1, 24, 3, 3)
+        return smpl(betas=p[:, 3:13].contiguous(), body_pose=R[:, 1:], global_orient=R[:, :1], pose2rot=False).vertices
+    dv = (verts(para) - verts(ref)).norm(dim=-1)
+    u, v, i, a = out["visualization"]["iuv_pred"]
+    idx = i.argmax(1).cpu().numpy()
+    ann = a.argmax(1).cpu().numpy()
+    safe = g["index_margin"].astype(np.float32) > 1e-3
+    safe_a = g["ann_margin"].astype(np.float32) > 1e-3
+    nd = int(g["detail"])
+    parts = out["visualization"]["part_iuv_pred"][:nd, :, 2].argmax(2).cpu().numpy()
+    safe_p = g["part_margin"].astype(np.float32) > 1e-3
+    return {"golden": os.path.relpath(gp, ROOT), "images": B,
+            "para_max_abs_err": float((para - ref).abs().max()), "para_tolerance": 1e-4,
+            "stn_kps_max_abs_err": float((out["stn_kps_pred"].cpu() - torch.from_numpy(g["stn_kps"])).abs().max()),
+            "verts_max_err_mm": float(dv.max()) * 1e3, "verts_mean_err_mm": float(dv.mean()) * 1e3,
+            "index_argmax_agree_margin_gt_1e-3": float((idx == g["index_argmax"])[safe].mean()),
+            "index_argmax_agree_all": float((idx == g["index_argmax"]).mean()),
+            "ann_argmax_agree_margin_gt_1e-3": float((ann == g["ann_argmax"])[safe_a].mean()),
+            "part_argmax_agree_margin_gt_1e-3": float((parts == g["part_argmax"])[safe_p].mean()),
+            "part_argmax_agree_all": float((parts == g["part_argmax"]).mean())}
+
+
+def time_net(net, smpl, rend, x, iters):
+    """ms per call of infer_net + SMPL + render on a resident batch (CUDA events, graph replay)."""
+    import torch
+
+    def f():
+        para = net.infer_net(x)["para"]
+        R = para[:, 13:].reshape(-1, 24, 3, 3)
+        out = smpl(betas=para[:, 3:13].contiguous(), body_pose=R[:, 1:], global_orient=R[:, :1], pose2rot=False)
+        return rend.verts2uvimg(out.vertices, para[:, :3].contiguous())
+    for _ in range(3):
+        f()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        f()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
 
 
 def profile_step(net, plan, x, dev):
@@ -469,6 +552,7 @@ def main():
                     help="tensor-core path: exact = split-fp16 operands, 3 MMAs per K step (fp32-grade, default); fast = one fp16 pass")
     ap.add_argument("--no-group", action="store_true", help="one convolution per launch (no multi-problem launches)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the B=1 W32 latency line and the other-precision run")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -12,7 +12,7 @@ void set_error(const char* fmt, ...) {
 }  // namespace danet
 
 extern "C" const char* danet_last_error(void) { return danet::g_err; }
-extern "C" int danet_version(void) { return 2; }   // 2: danet_conv_desc.flags (fp16 activation buffers)
+extern "C" int danet_version(void) { return 3; }   // 3: danet_act views, danet_conv_tc_group (split-fp16 tensor-core engine)
 extern "C" int danet_device_info(int* sm_count, int* cc_major, int* cc_minor) {
     int dev = 0;
     DANET_CUDA(cudaGetDevice(&dev));

@@ -17,12 +17,13 @@ from .smpl import mpjpe_h36m
 
 
 @torch.no_grad()
-def evaluate_batch(model, smpl, images, gt_keypoints_3d_j14, group=None):
+def evaluate_batch(model, smpl, images, gt_keypoints_3d_j14, group=None, shard=True):
     """images [N,3,224,224]; gt_keypoints_3d_j14 [N,14,3] (pelvis-centred H36M joints in the
     H36M_TO_J14 order, eval.py:196-200).  Returns dict(mpjpe [N] in metres, pred_j14 [N,14,3],
-    para [N,229]) on every rank."""
+    para [N,229]) on every rank.  shard=False: evaluate all N images on this rank, no collective
+    (eval_h36m.run_evaluation deals whole batches to ranks instead)."""
     import torch.distributed as dist
-    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    world = dist.get_world_size(group) if shard and dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
     n = images.shape[0]
     lo, hi = shard_bounds(n, world, rank)
@@ -40,5 +41,7 @@ def evaluate_batch(model, smpl, images, gt_keypoints_3d_j14, group=None):
         para = torch.zeros(0, 229, device=dev)
         err = torch.zeros(0, device=dev)
         j14 = torch.zeros(0, 14, 3, device=dev)
+    if world == 1:
+        return {"mpjpe": err, "pred_j14": j14, "para": para}
     return {"mpjpe": gather_outputs(err, n, group), "pred_j14": gather_outputs(j14, n, group),
             "para": gather_outputs(para, n, group)}

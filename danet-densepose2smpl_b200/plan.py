@@ -262,7 +262,8 @@ class Plan(object):
     RP = "iuv2smpl.smpl_para_Outs."
 
     def __init__(self, graph, state_dict, B, device, conv_algo="simt", precision="exact", align_corners=False,
-                 vis_thresh=0.5, want_vis=True, ops=None, use_cuda_graph=False, group_convs=True, wcache=None):
+                 vis_thresh=0.5, want_vis=True, ops=None, use_cuda_graph=False, group_convs=True, wcache=None,
+                 keep_all=False):
         self.g, self.B, self.device = graph, B, torch.device(device)
         self.ops = ops if ops is not None else CudaOps(device)
         self.align_corners, self.vis_thresh, self.want_vis = align_corners, vis_thresh, want_vis
@@ -276,6 +277,7 @@ class Plan(object):
             raise RuntimeError("danet_b200: the tensor-core path is sm_100a code; device %s is not compute capability 10.x" % device)
         self.P = self.ops.planes(precision) if self.tc else 0          # fp16 planes per activation (0: fp32 buffers only)
         self.group_convs = group_convs and self.tc
+        self.keep_all = keep_all                      # debugging: no buffer reuse, every intermediate stays readable
         self.wcache = wcache if wcache is not None else {}
         self.n_launch = 0
         self.n_tc = 0
@@ -401,7 +403,7 @@ class Plan(object):
         self.buf = {}
         release_at = {}
         for name, idx in last_use.items():
-            if name not in keep:
+            if name not in keep and not self.keep_all:
                 release_at.setdefault(idx, []).append(name)
         by_step = {}
         for name, idx in produced.items():

@@ -122,7 +122,7 @@ def test_c_abi_exports_every_declared_symbol():
     from danet_b200 import _lib
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     l = _lib.load()
-    assert l.danet_version() == 2
+    assert l.danet_version() == 3
 
 
 def test_product_does_not_import_oracle():

@@ -32,6 +32,7 @@
 #include <cuda_fp16.h>
 #include <mutex>
 #include <string.h>
+#include <math.h>
 
 namespace danet {
 namespace tc {
@@ -44,6 +45,7 @@ constexpr int kNumEpi = kEpiWarps * 32;
 constexpr int kMaxAStages = 8, kMaxBStages = 8;
 constexpr int kSmemMax = 227 * 1024;                   // opt-in dynamic shared memory per CTA on sm_100
 constexpr int kSmemFixed = 2048;                       // barriers + 1024-byte alignment slack
+constexpr int kPackHeader = 1024;                      // packed weights start with a header: float[0] = 2^s applied to the weights, float[1] = 2^-s
 
 struct alignas(64) Prob {
     CUtensorMap tm[2];                   // input planes: hi, lo
@@ -169,7 +171,7 @@ static bool make_prob(const danet_conv_desc* d, int S_req, Prob* g) {
     {
         const int gph0 = (g->NT / 16 + 1) / 2;
         if (g->exact && !g->big && g->S * gph0 <= 4) {
-            g->lseg = env_int("DANET_TC_LSEG", 12);
+            g->lseg = env_int("DANET_TC_LSEG", 4);
             int cnt = 0, nseg = 0;
             for (int c = 0; c < g->nchunks; ++c) {
                 const int kreal = (d->Cin - c * g->KCH + 15) / 16, kmma = g->KCH / 16;
@@ -390,7 +392,7 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
                 const Prob& P = a.p[pi];
                 const TileCoord tc = decode_tile(P, tile - P.tile_base);
                 const int ws = tc.img - mdiv(tc.img, P.m_ws) * P.wsets;
-                const uint8_t* src = P.wpk + ((long long)ws * P.blocks_per_set + (long long)tc.nt * P.nblk) * P.b_block_bytes;
+                const uint8_t* src = P.wpk + kPackHeader + ((long long)ws * P.blocks_per_set + (long long)tc.nt * P.nblk) * P.b_block_bytes;
                 for (int b = 0; b < P.nblk; ++b) {
                     mbar_wait(bar_b_empty + 8 * bs, ((bph >> bs) & 1u) ^ 1u);
                     mbar_expect_tx(bar_b_full + 8 * bs, (uint32_t)P.b_block_bytes);
@@ -531,6 +533,9 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
             const __half* __restrict__ res_hi = (a.variant & 2) ? nullptr : P.res_hi;
             const __half* __restrict__ res_lo = P.res_lo;
             float* __restrict__ y_f = P.y_f; __half* __restrict__ y_hi = P.y_hi; __half* __restrict__ y_lo = P.y_lo;
+            // the packed weights carry a power-of-two scale 2^s (so that their lo halves are normal fp16 numbers): bias and
+            // residual enter the accumulator times 2^s and the sum leaves it times 2^-s -- exact in fp32
+            const float2 wsc = __ldg(reinterpret_cast<const float2*>(P.wpk));
             const int ngroups = NT >> 4;
             const int gph = (ngroups - half + 1) >> 1;            // groups this warp owns per sub-tile
             const int nunits = S * gph;
@@ -577,6 +582,8 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
                                 }
                             }
                         }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) ac[j] *= wsc.x;
                     }
                 }
                 // add every K segment of the tile from TMEM (a multi-batch tile has a single segment)
@@ -628,6 +635,8 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
                     for (int h = 0; h < 2; ++h) {
                         if (cou[uu] + 8 * h >= cw) continue;
                         float* ac = &acc[uu][8 * h];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) ac[j] *= wsc.y;
                         if (relu) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) ac[j] = fmaxf(ac[j], 0.f);
@@ -667,7 +676,20 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
 // weight packing: SIMT layout [wsets][ks*ks*Cin][Cout] fp32 -> swizzled smem-image blocks of split fp16.
 // block (ws, nt, chunk, parity plane, tap group[, plane]) = [TG taps][rows][SWB bytes]; rows = output channels
 // (nconcat: NT hi rows then NT lo rows; wsplit: a hi block followed by a lo block)
-__global__ void k_pack(const Prob g, const float* __restrict__ w, __half* __restrict__ out) {
+__global__ void k_absmax(long long n, const float* __restrict__ w, unsigned* __restrict__ out) {
+    unsigned m = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned b = __float_as_uint(fabsf(w[i]));
+        if (b < 0x7f800000u && b > m) m = b;           // finite values only; non-negative floats order like their bit patterns
+    }
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+__global__ void k_pack_header(float scale, float* __restrict__ hdr) {
+    if (threadIdx.x < kPackHeader / 4) hdr[threadIdx.x] = threadIdx.x == 0 ? scale : (threadIdx.x == 1 ? 1.0f / scale : 0.0f);
+}
+
+__global__ void k_pack(const Prob g, const float* __restrict__ w, __half* __restrict__ out, float scale) {
     const int blk_halves = g.b_block_bytes / 2;
     const long long total = (long long)g.wsets * g.blocks_per_set * blk_halves;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -696,7 +718,7 @@ __global__ void k_pack(const Prob g, const float* __restrict__ w, __half* __rest
             const int t = g.tapidx[slot][k];
             const int cin = c * g.KCH + kk;
             const int co = nt * g.NT + n;
-            if (co < g.Cout && cin < g.Cin) v = w[((size_t)ws * taps * g.Cin + (size_t)t * g.Cin + cin) * g.Cout + co];
+            if (co < g.Cout && cin < g.Cin) v = w[((size_t)ws * taps * g.Cin + (size_t)t * g.Cin + cin) * g.Cout + co] * scale;
         }
     }
     v = fminf(fmaxf(v, -65504.f), 65504.f);
@@ -866,15 +888,35 @@ extern "C" int danet_conv_tc_supported(const danet_conv_desc* d) {
 extern "C" int64_t danet_conv_tc_packed_bytes(const danet_conv_desc* d) {
     tc::Prob g;
     if (!d || !tc::make_prob(d, 1, &g)) return 0;
-    return (int64_t)d->wsets * g.blocks_per_set * g.b_block_bytes;
+    return tc::kPackHeader + (int64_t)d->wsets * g.blocks_per_set * g.b_block_bytes;
 }
 
 extern "C" int danet_conv_tc_pack(const danet_conv_desc* d, const float* w_simt, void* w_packed, danet_stream_t stream) {
     tc::Prob g;
     DANET_CHECK(d && tc::make_prob(d, 1, &g), "danet_conv_tc_pack: shape not supported by the tcgen05 path");
     DANET_CHECK(w_simt && w_packed, "danet_conv_tc_pack: null pointer");
+    // power-of-two scale that brings the largest |w| into [2^13, 2^14): the lo halves (2^-11 of the value) of all but
+    // the tiniest weights are then normal fp16 numbers and the split keeps its 22 bits
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned* d_max = nullptr;
+    DANET_CUDA(cudaMalloc((void**)&d_max, 4));
+    DANET_CUDA(cudaMemsetAsync(d_max, 0, 4, st));
+    const long long nw = (long long)d->wsets * d->ksize * d->ksize * d->Cin * d->Cout;
+    tc::k_absmax<<<148, 256, 0, st>>>(nw, w_simt, d_max);
+    unsigned h_max = 0;
+    DANET_CUDA(cudaMemcpyAsync(&h_max, d_max, 4, cudaMemcpyDeviceToHost, st));
+    DANET_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_max);
+    float wmax, scale = 1.0f;
+    memcpy(&wmax, &h_max, 4);
+    if (wmax > 0.0f) {
+        int e = 0;
+        frexpf(wmax, &e);                             // wmax = m * 2^e, m in [0.5, 1)
+        scale = ldexpf(1.0f, 14 - e);                // wmax * scale in [2^13, 2^14)
+    }
+    tc::k_pack_header<<<1, 256, 0, st>>>(scale, (float*)w_packed);
     const long long total = (long long)g.wsets * g.blocks_per_set * (g.b_block_bytes / 2);
-    tc::k_pack<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g, w_simt, (__half*)w_packed);
+    tc::k_pack<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g, w_simt, (__half*)((uint8_t*)w_packed + tc::kPackHeader), scale);
     DANET_LAUNCH_CHECK();
     return 0;
 }

@@ -38,4 +38,5 @@ for idx, op in enumerate(net.graph.ops):
     if desc == "conv":
         desc = "conv k%d s%d %d->%d @%d g%d%s" % (op["k"], op["stride"], op["x"].C, y.C, op["x"].H, op["groups"], " +res" if op["res"] is not None else "")
     print("%4d %-34s %-10s max|d|=%.3e max|v|=%.3e rel=%.2e mean_rel=%.2e%s" % (idx, desc, y.name, d.max().item(), scale, rel, mean_rel, flag))
-print("para diff:", (pa.out("para") - pb.out("para")).abs().max().item())
+pa_, pb_ = pa.buf[net.graph.outputs["para"].name], pb.buf[net.graph.outputs["para"].name]
+print("para diff:", (pa_.value().float() - pb_.value().float()).abs().max().item())

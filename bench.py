@@ -397,20 +397,26 @@ def parity_block(net, dev, width, B):
     u, v, i, a = out["visualization"]["iuv_pred"]
     idx = i.argmax(1).cpu().numpy()
     ann = a.argmax(1).cpu().numpy()
-    safe = g["index_margin"].astype(np.float32) > 1e-3
-    safe_a = g["ann_margin"].astype(np.float32) > 1e-3
-    nd = int(g["detail"])
-    parts = out["visualization"]["part_iuv_pred"][:nd, :, 2].argmax(2).cpu().numpy()
-    safe_p = g["part_margin"].astype(np.float32) > 1e-3
-    return {"golden": os.path.relpath(gp, ROOT), "images": B,
-            "para_max_abs_err": float((para - ref).abs().max()), "para_tolerance": 1e-4,
+    parts = out["visualization"]["part_iuv_pred"][:, :, 2].argmax(2).cpu().numpy()
+    tie = np.unpackbits(g["part_tie_bits"], axis=1)[:, :parts[0].size].reshape(parts.shape).astype(bool)
+    flip_i, flip_a, flip_p = idx != g["index_argmax"], ann != g["ann_argmax"], parts != g["part_argmax_all"]
+    bad = int((flip_i & (g["index_margin"].astype(np.float32) > 1e-3)).sum() + (flip_a & (g["ann_margin"].astype(np.float32) > 1e-3)).sum()
+              + (flip_p & ~tie).sum())
+    dirty = flip_i.reshape(B, -1).any(1) | flip_p.reshape(B, -1).any(1)
+    err = (para - ref).abs().max(1)[0].cpu().numpy()
+    dvn = dv.max(1)[0].cpu().numpy() * 1e3
+    return {"golden": os.path.relpath(gp, ROOT), "images": B, "para_tolerance": 1e-4,
+            "note": "integer decisions (iuvmap_clean argmax) may flip only where the REFERENCE's own top-2 margin is < 1e-3 "
+                    "(near-ties); images whose integer maps equal the reference's are held to the 1e-4 tolerance",
+            "images_with_identical_integer_maps": int((~dirty).sum()),
+            "para_max_abs_err_identical_maps": float(err[~dirty].max()) if (~dirty).any() else None,
+            "verts_max_err_mm_identical_maps": float(dvn[~dirty].max()) if (~dirty).any() else None,
+            "images_with_near_tie_flips": int(dirty.sum()), "flipped_pixels_total": int(flip_i.sum() + flip_p.sum()),
+            "flips_outside_reference_near_ties": bad,
+            "para_max_abs_err_flipped_images": float(err[dirty].max()) if dirty.any() else 0.0,
+            "verts_max_err_mm_flipped_images": float(dvn[dirty].max()) if dirty.any() else 0.0,
             "stn_kps_max_abs_err": float((out["stn_kps_pred"].cpu() - torch.from_numpy(g["stn_kps"])).abs().max()),
-            "verts_max_err_mm": float(dv.max()) * 1e3, "verts_mean_err_mm": float(dv.mean()) * 1e3,
-            "index_argmax_agree_margin_gt_1e-3": float((idx == g["index_argmax"])[safe].mean()),
-            "index_argmax_agree_all": float((idx == g["index_argmax"]).mean()),
-            "ann_argmax_agree_margin_gt_1e-3": float((ann == g["ann_argmax"])[safe_a].mean()),
-            "part_argmax_agree_margin_gt_1e-3": float((parts == g["part_argmax"])[safe_p].mean()),
-            "part_argmax_agree_all": float((parts == g["part_argmax"]).mean())}
+            "verts_mean_err_mm": float(dv.mean()) * 1e3}
 
 
 def time_net(net, smpl, rend, x, iters):

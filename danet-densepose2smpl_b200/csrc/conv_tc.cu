@@ -45,6 +45,8 @@ constexpr int kNumEpi = kEpiWarps * 32;
 constexpr int kMaxAStages = 8, kMaxBStages = 8;
 constexpr int kSmemMax = 227 * 1024;                   // opt-in dynamic shared memory per CTA on sm_100
 constexpr int kSmemFixed = 2048;                       // barriers + 1024-byte alignment slack
+constexpr int kSchedDepth = 4;
+constexpr int kSchedConsumers = 2 + kEpiWarps;         // B producer, MMA warp, one lane per epilogue warp
 constexpr int kPackHeader = 1024;                      // packed weights start with a header: float[0] = 2^s applied to the weights, float[1] = 2^-s
 
 struct alignas(64) Prob {
@@ -78,7 +80,7 @@ constexpr int kMaxProb = 6;
 struct ArgsN {
     int nprob, total_tiles, na_stages, a_slot_bytes, nb_stages, b_slot_bytes;
     int variant, pad_;                   // bring-up knock-outs (DANET_TC_VARIANT): 1 no stores, 2 no residual/bias loads, 4 no MMAs
-    long long* prof;
+    unsigned* sched;                     // [2]: dynamic tile counter, finished-CTA counter (self-resetting); NULL = static round-robin
     Prob p[kMaxProb];
 };
 
@@ -171,7 +173,7 @@ static bool make_prob(const danet_conv_desc* d, int S_req, Prob* g) {
     {
         const int gph0 = (g->NT / 16 + 1) / 2;
         if (g->exact && !g->big && g->S * gph0 <= 4) {
-            g->lseg = env_int("DANET_TC_LSEG", 4);
+            g->lseg = env_int("DANET_TC_LSEG", 8);
             int cnt = 0, nseg = 0;
             for (int c = 0; c < g->nchunks; ++c) {
                 const int kreal = (d->Cin - c * g->KCH + 15) / 16, kmma = g->KCH / 16;
@@ -315,6 +317,16 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes
 __host__ __device__ __forceinline__ uint32_t swz(uint32_t off, uint32_t mask) { return off ^ (((off >> 7) & mask) << 4); }
 __device__ __forceinline__ int mdiv(int x, unsigned long long m) { return (int)(((unsigned long long)(unsigned)x * m) >> 40); }
 
+// consumer side of the tile ring: one lane waits for slot `seq`, reads the tile index and frees the slot
+__device__ __forceinline__ int sched_next(uint32_t bar_full, uint32_t bar_empty, uint32_t ring, int seq) {
+    const int slot = seq & (kSchedDepth - 1);
+    mbar_wait(bar_full + 8 * slot, (seq / kSchedDepth) & 1);
+    int tile;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(tile) : "r"(ring + 4 * slot) : "memory");
+    mbar_arrive(bar_empty + 8 * slot);
+    return tile;
+}
+
 struct TileCoord { int nt, tw, th, img; };
 __device__ __forceinline__ TileCoord decode_tile(const Prob& g, int t) {
     TileCoord c;
@@ -339,12 +351,16 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
     const uint32_t bar_b_full = sBar + 16 * kMaxAStages, bar_b_empty = bar_b_full + 8 * kMaxBStages;
     const uint32_t bar_acc_full = bar_b_empty + 8 * kMaxBStages, bar_acc_empty = bar_acc_full + 16;
     const uint32_t tmem_slot_addr = bar_acc_empty + 16;
+    // dynamic tile scheduler: a ring of kSchedDepth tile indices published by the A producer (it takes them from a
+    // global atomic counter, heaviest problems first) and read by the other roles
+    const uint32_t bar_sched_full = sBar + 512, bar_sched_empty = sBar + 512 + 8 * kSchedDepth, sched_ring = sBar + 512 + 16 * kSchedDepth;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full + 8 * i, 1); mbar_init(bar_acc_empty + 8 * i, kNumEpi); }
         for (int i = 0; i < a.na_stages; ++i) { mbar_init(bar_a_full + 8 * i, 1); mbar_init(bar_a_empty + 8 * i, 1); }
         for (int i = 0; i < a.nb_stages; ++i) { mbar_init(bar_b_full + 8 * i, 1); mbar_init(bar_b_empty + 8 * i, 1); }
+        for (int i = 0; i < kSchedDepth; ++i) { mbar_init(bar_sched_full + 8 * i, 1); mbar_init(bar_sched_empty + 8 * i, kSchedConsumers); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kWarpA && lane < a.nprob) { tma_prefetch_desc(&a.p[lane].tm[0]); if (a.p[lane].exact) tma_prefetch_desc(&a.p[lane].tm[1]); }
@@ -365,7 +381,17 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
             int as = 0; uint32_t aph = 0;
             int pi = 0;
             pdl_wait();                                              // activations come from the previous kernel
-            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+            int tile = blockIdx.x;
+            for (int seq = 0;; ++seq) {
+                // publish this tile (or the end marker) to the other roles, then take the next one from the global counter:
+                // the atomic's latency hides under the loads of the current tile
+                const int slot = seq & (kSchedDepth - 1);
+                mbar_wait(bar_sched_empty + 8 * slot, ((seq / kSchedDepth) & 1) ^ 1);
+                asm volatile("st.shared.s32 [%0], %1;" ::"r"(sched_ring + 4 * slot), "r"(tile) : "memory");
+                mbar_arrive(bar_sched_full + 8 * slot);
+                if (tile >= a.total_tiles) break;
+                const int next = a.sched ? (int)(atomicAdd(a.sched, 1u) + gridDim.x) : tile + (int)gridDim.x;
+                pi = 0;
                 while (tile >= a.p[pi].tile_base + a.p[pi].tile_count) ++pi;
                 const Prob& P = a.p[pi];
                 const TileCoord tc = decode_tile(P, tile - P.tile_base);
@@ -380,6 +406,7 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
                             aph ^= 1u << as;
                             if (++as == a.na_stages) as = 0;
                         }
+                tile = next;
             }
         }
     } else if (warp == kWarpB) {
@@ -387,7 +414,10 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
         if (lane == 0) {
             int bs = 0; uint32_t bph = 0;
             int pi = 0;
-            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+            for (int seq = 0;; ++seq) {
+                const int tile = sched_next(bar_sched_full, bar_sched_empty, sched_ring, seq);
+                if (tile >= a.total_tiles) break;
+                pi = 0;
                 while (tile >= a.p[pi].tile_base + a.p[pi].tile_count) ++pi;
                 const Prob& P = a.p[pi];
                 const TileCoord tc = decode_tile(P, tile - P.tile_base);
@@ -408,7 +438,12 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
         // elected lane issues the tcgen05 instructions.
         int as = 0, bs = 0; uint32_t aph = 0, bph = 0, eph = 0; int tog = 0;
         int pi = 0;
-        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        for (int seq = 0;; ++seq) {
+            int tile = 0;
+            if (lane == 0) tile = sched_next(bar_sched_full, bar_sched_empty, sched_ring, seq);
+            tile = __shfl_sync(0xffffffffu, tile, 0);
+            if (tile >= a.total_tiles) break;
+            pi = 0;
             while (tile >= a.p[pi].tile_base + a.p[pi].tile_count) ++pi;
             const Prob& P = a.p[pi];
             const TileCoord tc = decode_tile(P, tile - P.tile_base);
@@ -522,7 +557,12 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
         int pi = 0;
         const bool do_store = !(a.variant & 1);
         pdl_wait();                                              // residual reads / output writes
-        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        for (int seq = 0;; ++seq) {
+            int tile = 0;
+            if (lane == 0) tile = sched_next(bar_sched_full, bar_sched_empty, sched_ring, seq);
+            tile = __shfl_sync(0xffffffffu, tile, 0);
+            if (tile >= a.total_tiles) break;
+            pi = 0;
             while (tile >= a.p[pi].tile_base + a.p[pi].tile_count) ++pi;
             const Prob& P = a.p[pi];
             const TileCoord tc = decode_tile(P, tile - P.tile_base);
@@ -667,6 +707,11 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
     }
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0 && a.sched) {
+        // the last CTA to finish re-arms the scheduler for the next launch (or graph replay) that uses this slot
+        __threadfence();
+        if (atomicAdd(a.sched + 1, 1u) == gridDim.x - 1) { a.sched[0] = 0u; a.sched[1] = 0u; __threadfence(); }
+    }
     if (warp == kWarpMma) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -783,6 +828,9 @@ static int encode_x(const Prob& g, const void* base, CUtensorMap* tm) {
 }  // namespace tc
 
 static int g_sm_count[64];
+static unsigned* g_sched[64];              // per device: kSchedSlots x {tile counter, done counter}, zero-initialised, self-resetting
+static unsigned g_sched_seq[64];
+constexpr int kSchedSlots = 1024;
 static std::mutex g_tc_mu;
 static unsigned long long g_tc_devs = 0;
 static bool g_use_pdl = true;
@@ -841,7 +889,6 @@ int conv_tc_group_launch(int n, const danet_conv_problem* probs, cudaStream_t st
         DANET_CHECK(base < (1 << 24), "danet_conv_tc_group: too many tiles");
     }
     a.total_tiles = base;
-    a.prof = nullptr;
     a.variant = env_int("DANET_TC_VARIANT", 0);
     int dev = 0;
     DANET_CUDA(cudaGetDevice(&dev));
@@ -852,7 +899,11 @@ int conv_tc_group_launch(int n, const danet_conv_problem* probs, cudaStream_t st
             DANET_CUDA(cudaDeviceGetAttribute(&g_sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
             DANET_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
             g_use_pdl = env_int("DANET_TC_PDL", 1) != 0;
+            DANET_CUDA(cudaMalloc((void**)&g_sched[dev], kSchedSlots * 2 * sizeof(unsigned)));
+            DANET_CUDA(cudaMemset(g_sched[dev], 0, kSchedSlots * 2 * sizeof(unsigned)));
         }
+        // every launch takes the next counter pair (a CUDA graph keeps the one it captured: the kernel re-arms it)
+        a.sched = env_int("DANET_TC_DYNAMIC", 1) ? g_sched[dev] + 2 * (g_sched_seq[dev]++ % kSchedSlots) : nullptr;
     }
     const int smem_bytes = kSmemFixed + a.na_stages * a.a_slot_bytes + a.nb_stages * a.b_slot_bytes;
     const int cap = g_sm_count[dev];

@@ -47,14 +47,14 @@ def iuv_map2img(U_uv, V_uv, Index_UV, AnnIndex=None, uv_rois=None, ind_mapping=N
     idx = torch.argmax(Index_UV, dim=1)
     if AnnIndex is not None:
         idx = idx * (torch.argmax(AnnIndex, dim=1) > 0).to(torch.int64)
-    out0 = idx.to(torch.float32)
+    # the index channel through a K-entry table built on the host with IEEE division / multiplication: torch's CUDA
+    # division by a scalar multiplies by the reciprocal, which is one ulp off the reference's CPU result for some k
     if ind_mapping is None:
-        out0 = out0 / float(K - 1)
+        full = torch.arange(K, dtype=torch.float32) / float(K - 1)
     else:
-        lut = torch.tensor([m * (1. / 24.) for m in ind_mapping], device=idx.device, dtype=torch.float32)
-        full = torch.arange(K, device=idx.device, dtype=torch.float32)
-        full[:len(ind_mapping)] = lut
-        out0 = full[idx]
+        full = torch.arange(K, dtype=torch.float32)
+        full[:len(ind_mapping)] = torch.tensor([m * (1. / 24.) for m in ind_mapping], dtype=torch.float32)
+    out0 = full.to(idx.device)[idx]
     u = torch.gather(U_uv, 1, idx.unsqueeze(1)).squeeze(1) * (idx > 0)
     v = torch.gather(V_uv, 1, idx.unsqueeze(1)).squeeze(1) * (idx > 0)
     return torch.stack([out0, u, v], dim=1)

@@ -63,10 +63,16 @@ def gen(ns, width, B, seed, detail=None, chunk=8):
             para=r["para"].numpy(), stn_kps=ret["stn_kps_pred"].numpy(),
             index_argmax=I_raw.argmax(1).numpy().astype(np.uint8), index_margin=top2_margin(I_raw).numpy().astype(np.float16),
             ann_argmax=A_raw.argmax(1).numpy().astype(np.uint8), ann_margin=top2_margin(A_raw).numpy().astype(np.float16))
+        pm = top2_margin(pp[:, :, 2], dim=2)
+        if detail is not None:
+            # every image: the per-part argmax maps and, bit-packed, where the reference's own top-2 margin is below 1e-3
+            # (near-ties: any implementation may pick the other index there, and the regressor's output then moves)
+            part.update(part_argmax_all=pp[:, :, 2].argmax(2).numpy().astype(np.uint8),
+                        part_tie_bits=np.packbits((pm < 1e-3).numpy().reshape(pm.shape[0], -1), axis=1))
         if s0 < nd:
             part.update(
                 part_argmax=pp[:, :, 2].argmax(2).numpy().astype(np.uint8),
-                part_margin=top2_margin(pp[:, :, 2], dim=2).numpy().astype(np.float16),
+                part_margin=pm.numpy().astype(np.float16),
                 u_sum=u.sum(1).numpy().astype(np.float32), v_sum=v.sum(1).numpy().astype(np.float32))
             if detail is None:
                 part.update(

@@ -57,6 +57,8 @@ SIGNATURES = {
     "danet_smpl_destroy": (c_int, [c_p]),
     "danet_smpl_workspace_bytes": (c_i64, [c_p, c_int]),
     "danet_smpl_forward": (c_int, [c_p, c_int, c_p, c_p, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_p]),
+    "danet_smpl_backward_workspace_bytes": (c_i64, [c_p, c_int]),
+    "danet_smpl_backward": (c_int, [c_p, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "danet_rot6d_to_rotmat": (c_int, [c_int, c_p, c_p, c_p]),
     "danet_batch_rodrigues": (c_int, [c_int, c_p, c_p, c_int, c_p]),
     "danet_perspective_projection": (c_int, [c_int, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),

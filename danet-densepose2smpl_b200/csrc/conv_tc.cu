@@ -45,7 +45,7 @@ constexpr int kNumEpi = kEpiWarps * 32;
 constexpr int kMaxAStages = 8, kMaxBStages = 8;
 constexpr int kSmemMax = 227 * 1024;                   // opt-in dynamic shared memory per CTA on sm_100
 constexpr int kSmemFixed = 2048;                       // barriers + 1024-byte alignment slack
-constexpr int kSchedDepth = 4;
+constexpr int kSchedDepth = 4, kSchedAhead = 2, kSchedStatic = 3;
 constexpr int kSchedConsumers = 2 + kEpiWarps;         // B producer, MMA warp, one lane per epilogue warp
 constexpr int kPackHeader = 1024;                      // packed weights start with a header: float[0] = 2^s applied to the weights, float[1] = 2^-s
 
@@ -63,6 +63,8 @@ struct alignas(64) Prob {
     int nconcat;                         // exact mode: hi and lo weight rows share one block (one MMA of width 2*NT)
     int ACC;                             // accumulator columns per sub-tile
     int big;                             // S*ACC > 256: the tile takes both accumulator halves
+    int nstack, hs, box_h;               // small maps: nstack images share one tile; image n's rows start at group n*hs
+                                         // (hs = H + pad: the zero rows between images are the TMA out-of-bounds fill)
     int lseg, nseg;                      // K segmentation: close a segment after a weight block once it holds >= lseg
                                          // main-chain MMAs; nseg segments per tile (1 in fast mode)
     int par_py[4], par_px[4], ntap[4], ngrp[4], stage_bytes[4], sbo_a[4];
@@ -137,6 +139,16 @@ static bool make_prob(const danet_conv_desc* d, int S_req, Prob* g) {
         }
     // every parity plane is loaded with the box of the largest one (one tensor map per input plane)
     const int Hb = kTileH + tr_max - 1, Wb = kTileW * S + tc_max - 1;
+    // Small maps (H + pad <= 8): several images share the 16 row groups of a tile.  Image n of the tile is loaded by its
+    // own TMA box [(H + 2 pad) rows] at row offset n * (H + pad): the bottom halo of one image and the top halo of the
+    // next are the same shared-memory rows, both filled with out-of-bounds zeros.  Row groups that fall on those rows
+    // produce garbage outputs the epilogue never stores.  Needs one weight set (consecutive images share weights).
+    g->nstack = 1; g->hs = kTileH; g->box_h = Hb;
+    if (d->stride == 1 && d->wsets == 1 && d->H + d->pad <= kTileH / 2 && env_int("DANET_TC_STACK", 1)) {
+        g->hs = d->H + d->pad;
+        g->nstack = kTileH / g->hs;
+        g->box_h = d->H + 2 * d->pad;
+    }
     // swizzle width: the widest row unless the channel count is tiny
     int swb = 128;
     const int c16 = (d->Cin + 15) / 16 * 16;
@@ -191,7 +203,7 @@ static bool make_prob(const danet_conv_desc* d, int S_req, Prob* g) {
     }
     g->blocks_per_set = (long long)g->ntn * g->nblk;
     g->tiles_w = (g->Wo + kTileW * S - 1) / (kTileW * S); g->tiles_h = (g->Ho + kTileH - 1) / kTileH;
-    const long long tiles = (long long)d->N * g->tiles_h * g->tiles_w * g->ntn;
+    const long long tiles = (long long)((d->N + g->nstack - 1) / g->nstack) * g->tiles_h * g->tiles_w * g->ntn;
     if (tiles >= (1 << 24) || g->wsets >= (1 << 16)) return false;
     if ((long long)d->N * g->Ho * g->Wo * d->Cout >= (1LL << 31) || (long long)d->N * d->H * d->W * d->Cin >= (1LL << 31)) return false;   // 32-bit element offsets
     g->tile_count = (int)tiles; g->tile_base = 0;
@@ -380,17 +392,27 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
         if (lane == 0) {
             int as = 0; uint32_t aph = 0;
             int pi = 0;
-            pdl_wait();                                              // activations come from the previous kernel
-            int tile = blockIdx.x;
+            // Tile scheduler: this thread publishes tile indices kSchedAhead tiles ahead of its own loads, so that the
+            // weight producer can prefetch for the coming tiles while the MMAs work on the current one.  The first
+            // kSchedStatic tiles of a CTA are its round-robin share (no atomic latency at start-up), later ones come
+            // from the global counter (heaviest problems first): greedy list scheduling over heterogeneous tiles.
+            int pub = 0; bool ended = false;
             for (int seq = 0;; ++seq) {
-                // publish this tile (or the end marker) to the other roles, then take the next one from the global counter:
-                // the atomic's latency hides under the loads of the current tile
-                const int slot = seq & (kSchedDepth - 1);
-                mbar_wait(bar_sched_empty + 8 * slot, ((seq / kSchedDepth) & 1) ^ 1);
-                asm volatile("st.shared.s32 [%0], %1;" ::"r"(sched_ring + 4 * slot), "r"(tile) : "memory");
-                mbar_arrive(bar_sched_full + 8 * slot);
+                while (pub <= seq + kSchedAhead && !ended) {
+                    const int slot = pub & (kSchedDepth - 1);
+                    mbar_wait(bar_sched_empty + 8 * slot, ((pub / kSchedDepth) & 1) ^ 1);
+                    int t;
+                    if (pub < kSchedStatic || !a.sched) t = (int)blockIdx.x + pub * (int)gridDim.x;
+                    else t = (int)atomicAdd(a.sched, 1u) + kSchedStatic * (int)gridDim.x;
+                    if (t >= a.total_tiles) { t = a.total_tiles; ended = true; }
+                    asm volatile("st.shared.s32 [%0], %1;" ::"r"(sched_ring + 4 * slot), "r"(t) : "memory");
+                    mbar_arrive(bar_sched_full + 8 * slot);
+                    ++pub;
+                }
+                int tile;
+                asm volatile("ld.shared.s32 %0, [%1];" : "=r"(tile) : "r"(sched_ring + 4 * (seq & (kSchedDepth - 1))) : "memory");
                 if (tile >= a.total_tiles) break;
-                const int next = a.sched ? (int)(atomicAdd(a.sched, 1u) + gridDim.x) : tile + (int)gridDim.x;
+                if (seq == 0) pdl_wait();                            // activations come from the previous kernel
                 pi = 0;
                 while (tile >= a.p[pi].tile_base + a.p[pi].tile_count) ++pi;
                 const Prob& P = a.p[pi];
@@ -400,13 +422,20 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
                     for (int slot = 0; slot < P.npa; ++slot)
                         for (int pl = 0; pl <= P.exact; ++pl) {
                             mbar_wait(bar_a_empty + 8 * as, ((aph >> as) & 1u) ^ 1u);
+                            if (P.nstack > 1) {
+                                const uint32_t box_bytes = (uint32_t)(P.box_h * P.sbo_a[slot]);
+                                mbar_expect_tx(bar_a_full + 8 * as, box_bytes * P.nstack);
+                                for (int n = 0; n < P.nstack; ++n)       // images beyond N are out of bounds: zero rows
+                                    tma_load_4d(sA + as * a.a_slot_bytes + n * P.hs * P.sbo_a[slot], &P.tm[pl], c * P.KCH, w0, -P.pad,
+                                                tc.img * P.nstack + n, bar_a_full + 8 * as);
+                            } else {
                             mbar_expect_tx(bar_a_full + 8 * as, (uint32_t)P.stage_bytes[slot]);
                             tma_load_4d(sA + as * a.a_slot_bytes, &P.tm[pl], c * P.KCH, w0 + P.par_px[slot], h0 + P.par_py[slot],
                                         tc.img, bar_a_full + 8 * as);
+                            }
                             aph ^= 1u << as;
                             if (++as == a.na_stages) as = 0;
                         }
-                tile = next;
             }
         }
     } else if (warp == kWarpB) {
@@ -580,9 +609,17 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
             const int gph = (ngroups - half + 1) >> 1;            // groups this warp owns per sub-tile
             const int nunits = S * gph;
             const int cw = Cout - tc.nt * NT;                     // channels of this N tile that exist (multiple of 8)
-            const int oh = tc.th * kTileH + prow;
-            const int boff = (tc.img - mdiv(tc.img, P.m_ws) * P.wsets) * Cout + tc.nt * NT;
-            const uint32_t rowbase = (uint32_t)(tc.img * Ho + oh) * Wo;
+            // this thread's output row: tile row prow of image tc.img, or (stacked small maps) row prow % hs of image
+            // tc.img * nstack + prow / hs -- rows hs-pad.. of a stacked image are the shared zero rows (no output)
+            int oh = tc.th * kTileH + prow, img = tc.img;
+            bool row_ok = oh < Ho;
+            if (P.nstack > 1) {
+                const int n = prow / P.hs;
+                oh = prow - n * P.hs; img = tc.img * P.nstack + n;
+                row_ok = oh < Ho && n < P.nstack && img < P.N;
+            }
+            const int boff = (img - mdiv(img, P.m_ws) * P.wsets) * Cout + tc.nt * NT;
+            const uint32_t rowbase = (uint32_t)(img * Ho + oh) * Wo;
             const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
             int cs_first = 0;
             for (int u0 = 0; u0 < (nunits > 0 ? nunits : 1); u0 += 4) {
@@ -594,7 +631,7 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
                     const int s = u / gph, grp = half + 2 * (u - s * gph);
                     const int ow = (tc.tw * S + s) * kTileW + pcol;
                     cou[uu] = grp * 16;
-                    okp[uu] = u < nunits && oh < Ho && ow < Wo;
+                    okp[uu] = u < nunits && row_ok && ow < Wo;
                     eoff[uu] = (rowbase + ow) * Cout + tc.nt * NT + grp * 16;
                     // accumulator <- bias (+ residual)
 #pragma unroll
@@ -814,7 +851,7 @@ static int encode_x(const Prob& g, const void* base, CUtensorMap* tm) {
     DANET_CHECK(((uintptr_t)base & 15) == 0, "conv_tc: activation plane must be 16-byte aligned");
     cuuint64_t gdim[4] = {(cuuint64_t)g.Cin, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.N};
     cuuint64_t gstr[3] = {(cuuint64_t)g.Cin * 2, (cuuint64_t)g.W * g.Cin * 2, (cuuint64_t)g.H * g.W * g.Cin * 2};
-    const int Wb = g.sbo_a[0] / g.SWB, Hb = g.stage_bytes[0] / g.sbo_a[0];
+    const int Wb = g.sbo_a[0] / g.SWB, Hb = g.box_h;
     cuuint32_t box[4] = {(cuuint32_t)g.KCH, (cuuint32_t)(g.stride * (Wb - 1) + 1), (cuuint32_t)(g.stride * (Hb - 1) + 1), 1u};
     cuuint32_t estr[4] = {1u, (cuuint32_t)g.stride, (cuuint32_t)g.stride, 1u};
     const CUtensorMapSwizzle sw = g.SWB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (g.SWB == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);

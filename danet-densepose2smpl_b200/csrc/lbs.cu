@@ -234,6 +234,7 @@ __global__ void k_smpl_pose(int B, int pose_kind, const float* __restrict__ beta
             }
         }
         for (int e = 0; e < 12; ++e) Gb[i * 12 + e] = g[e];
+        if (G) for (int e = 0; e < 12; ++e) G[((size_t)b * kJ + i) * 12 + e] = g[e];      // world transforms (backward pass)
         for (int r = 0; r < 3; ++r) {
             posed[((size_t)b * kJ + i) * 3 + r] = g[r * 4 + 3];
             Ab[i * 12 + r * 4 + 0] = g[r * 4 + 0];
@@ -467,6 +468,150 @@ __global__ void k_smpl_joints(int B, SmplView m, const float* __restrict__ posed
             joints_h36m[(size_t)b * m.nh36m * 3 + t] = s_j[(kJ + m.nsel + m.nextra) * 3 + t];
 }
 
+// ---------------------------------------------------------------------------------------------
+// backward of the SMPL layer (the piece of the training step, train/trainer.py:148-215 + smpl_regressor.py:131-221,
+// that has a hard oracle): given dL/dverts and dL/d(smpl joints), dL/dbetas and dL/dR (R = the 24 rotation matrices
+// the layer consumed, pose2rot=False).  fp32 SIMT; everything is recomputed from (betas, R), nothing is kept from
+// the forward pass.
+//   k_smpl_pose          (forward kernel) -> G (world transforms), A (skinning transforms), pose feature
+//   k_lbs_bwd_verts      grid (vertex tile, body): recompute v_posed, dv_posed = T_v^T g, dA += w (g x [v_posed;1])
+//   k_lbs_bwd_blend      dpf = P dv_posed (207 rows), dbeta_shape = S dv_posed: one warp per (body, row)
+//   k_lbs_bwd_chain      one thread per body: reverse kinematic chain -> dR, dJ -> dbeta
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTileV)
+k_lbs_bwd_verts(int B, const float* __restrict__ betas, const float* __restrict__ pf, const float* __restrict__ A,
+                SmplView m, const float* __restrict__ gverts, float* __restrict__ dvp, float* __restrict__ dA) {
+    __shared__ float s_pf[kPF];
+    __shared__ float s_A[kJ * 12];
+    __shared__ float s_dA[kJ * 12];
+    __shared__ float s_v[kTileC];
+    __shared__ float s_beta[kMaxBetas];
+    const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    for (int i = tid; i < kPF; i += kTileV) s_pf[i] = pf[(size_t)b * kPF + i];
+    for (int i = tid; i < kJ * 12; i += kTileV) { s_A[i] = A[(size_t)b * kJ * 12 + i]; s_dA[i] = 0.f; }
+    if (tid < kMaxBetas) s_beta[tid] = tid < m.nbetas ? betas[(size_t)b * m.nbetas + tid] : 0.f;
+    __syncthreads();
+    // v_posed of the tile (coordinate-parallel, like the forward pass)
+    const size_t n0 = (size_t)tile * kTileC + tid;
+    for (int j = 0; j < 3; ++j) {
+        const size_t n = n0 + j * kTileV;
+        float acc = __ldg(m.vt + n);
+        for (int l = 0; l < m.nbetas; ++l) acc = fmaf(s_beta[l], __ldg(m.sd + (size_t)l * m.npad + n), acc);
+        for (int k = 0; k < 207; ++k) acc = fmaf(s_pf[k], __ldg(m.pd + (size_t)k * m.npad + n), acc);
+        s_v[tid + j * kTileV] = acc;
+    }
+    __syncthreads();
+    const int v = tile * kTileV + tid;
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    if (v < m.nv) {
+        gx = gverts[((size_t)b * m.nv + v) * 3]; gy = gverts[((size_t)b * m.nv + v) * 3 + 1]; gz = gverts[((size_t)b * m.nv + v) * 3 + 2];
+    }
+    const float x = s_v[3 * tid], y = s_v[3 * tid + 1], z = s_v[3 * tid + 2];
+    float T[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float g[3] = {gx, gy, gz};
+    const float vh[4] = {x, y, z, 1.0f};
+    for (int j = 0; j < kJ; ++j) {
+        float w = 0.f;
+        if (m.skin_packed) {
+            const uint32_t idx = __ldg(m.skin_idx + v);
+            const float4 ww = __ldg(m.skin_w + v);
+            if ((int)(idx & 255) == j) w += ww.x;
+            if ((int)((idx >> 8) & 255) == j) w += ww.y;
+            if ((int)((idx >> 16) & 255) == j) w += ww.z;
+            if ((int)(idx >> 24) == j) w += ww.w;
+        } else {
+            w = __ldg(m.skin_dense + (size_t)j * m.nvpad + v);
+        }
+        if (w == 0.f || v >= m.nv) continue;
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) T[r * 3 + c] = fmaf(w, s_A[j * 12 + r * 4 + c], T[r * 3 + c]);
+            for (int c = 0; c < 4; ++c) atomicAdd(&s_dA[j * 12 + r * 4 + c], w * g[r] * vh[c]);
+        }
+    }
+    // dv_posed = T^T g
+    if (v < m.nv)
+        for (int c = 0; c < 3; ++c)
+            dvp[(size_t)b * m.npad + 3 * v + c] = T[c] * g[0] + T[3 + c] * g[1] + T[6 + c] * g[2];
+    else if (3 * v + 2 < m.npad)
+        for (int c = 0; c < 3; ++c) dvp[(size_t)b * m.npad + 3 * v + c] = 0.f;
+    __syncthreads();
+    for (int i = tid; i < kJ * 12; i += kTileV) if (s_dA[i] != 0.f) atomicAdd(&dA[(size_t)b * kJ * 12 + i], s_dA[i]);
+}
+
+// rows 0..206: dL/dpose_feature; rows 207..207+nbetas-1: dL/dbeta through the shape blend shapes
+__global__ void k_lbs_bwd_blend(int B, SmplView m, const float* __restrict__ dvp, float* __restrict__ dpf, float* __restrict__ dbeta) {
+    const int nrow = 207 + m.nbetas;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (gw >= B * nrow) return;
+    const int b = gw / nrow, r = gw % nrow;
+    const float* row = r < 207 ? m.pd + (size_t)r * m.npad : m.sd + (size_t)(r - 207) * m.npad;
+    const float* d = dvp + (size_t)b * m.npad;
+    float s = 0.f;
+    for (int n = lane; n < m.nv * 3; n += 32) s = fmaf(__ldg(row + n), d[n], s);
+    s = warp_sum(s);
+    if (lane == 0) { if (r < 207) dpf[(size_t)b * kPF + r] = s; else dbeta[(size_t)b * m.nbetas + (r - 207)] = s; }
+}
+
+__global__ void k_lbs_bwd_chain(int B, SmplView m, const float* __restrict__ betas, const float* __restrict__ R,
+                                const float* __restrict__ G, const float* __restrict__ dA, const float* __restrict__ dpf,
+                                const float* __restrict__ gjoints, float* __restrict__ dbeta, float* __restrict__ dR) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float J[kJ * 3];
+    for (int e = 0; e < kJ * 3; ++e) {
+        float v = m.Jt[e];
+        for (int l = 0; l < m.nbetas; ++l) v = fmaf(betas[(size_t)b * m.nbetas + l], m.Jsd[e * m.nbetas + l], v);
+        J[e] = v;
+    }
+    float dRg[kJ][9], dtg[kJ][3], dJ[kJ * 3];
+    const float* Gb = G + (size_t)b * kJ * 12;
+    for (int i = 0; i < kJ; ++i) {
+        const float* a = dA + ((size_t)b * kJ + i) * 12;
+        // A_i = [Rg_i | tg_i - Rg_i J_i]
+        for (int r = 0; r < 3; ++r) {
+            const float at = a[r * 4 + 3];
+            for (int c = 0; c < 3; ++c) dRg[i][r * 3 + c] = a[r * 4 + c] - at * J[i * 3 + c];
+            dtg[i][r] = at + (gjoints ? gjoints[((size_t)b * kJ + i) * 3 + r] : 0.f);
+        }
+        for (int c = 0; c < 3; ++c)
+            dJ[i * 3 + c] = -(Gb[i * 12 + 0 * 4 + c] * a[3] + Gb[i * 12 + 1 * 4 + c] * a[7] + Gb[i * 12 + 2 * 4 + c] * a[11]);
+    }
+    for (int i = kJ - 1; i >= 0; --i) {
+        const float* Ri = R + ((size_t)b * kJ + i) * 9;
+        float* out = dR + ((size_t)b * kJ + i) * 9;
+        if (i == 0) {
+            // G_0 = [R_0 | J_0]
+            for (int e = 0; e < 9; ++e) out[e] = dRg[0][e];
+            for (int c = 0; c < 3; ++c) dJ[c] += dtg[0][c];
+            break;
+        }
+        const int p = m.parents[i];
+        const float* Gp = Gb + p * 12;
+        const float rel[3] = {J[i * 3] - J[p * 3], J[i * 3 + 1] - J[p * 3 + 1], J[i * 3 + 2] - J[p * 3 + 2]};
+        // Rg_i = Rg_p R_i ; tg_i = Rg_p rel + tg_p
+        float dRi[9], drel[3];
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c)
+                dRi[r * 3 + c] = Gp[0 * 4 + r] * dRg[i][0 * 3 + c] + Gp[1 * 4 + r] * dRg[i][1 * 3 + c] + Gp[2 * 4 + r] * dRg[i][2 * 3 + c];
+        for (int r = 0; r < 3; ++r)
+            drel[r] = Gp[0 * 4 + r] * dtg[i][0] + Gp[1 * 4 + r] * dtg[i][1] + Gp[2 * 4 + r] * dtg[i][2];
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c)
+                dRg[p][r * 3 + c] += dRg[i][r * 3 + 0] * Ri[c * 3 + 0] + dRg[i][r * 3 + 1] * Ri[c * 3 + 1] + dRg[i][r * 3 + 2] * Ri[c * 3 + 2]
+                                     + dtg[i][r] * rel[c];
+            dtg[p][r] += dtg[i][r];
+        }
+        for (int c = 0; c < 3; ++c) { dJ[i * 3 + c] += drel[c]; dJ[p * 3 + c] -= drel[c]; }
+        // pose feature = vec(R_i - I), i >= 1
+        for (int e = 0; e < 9; ++e) out[e] = dRi[e] + dpf[(size_t)b * kPF + (i - 1) * 9 + e];
+    }
+    for (int l = 0; l < m.nbetas; ++l) {
+        float s = dbeta[(size_t)b * m.nbetas + l];
+        for (int e = 0; e < kJ * 3; ++e) s = fmaf(dJ[e], m.Jsd[e * m.nbetas + l], s);
+        dbeta[(size_t)b * m.nbetas + l] = s;
+    }
+}
+
 template <typename T>
 static int up(danet_smpl* h, const T** dst, const std::vector<T>& src) {
     T* d = nullptr;
@@ -673,7 +818,8 @@ extern "C" int danet_smpl_forward(danet_smpl_t h, int32_t B, const float* betas,
         feat_lo = (__half*)(ws + ws_off(cur, Bp * kGF * 2));
         vposed = (float*)(ws + ws_off(cur, (int64_t)(B < kGemmChunk ? Bp : kGemmChunk) * h->gemm_cout * 4));
     }
-    k_smpl_pose<<<cdiv(B, 32), 32, 0, stream>>>(B, pose_kind, betas, pose, m, rotmats, G, A, pf, posed, feat_hi, feat_lo);
+    k_smpl_pose<<<cdiv(B, 32), 32, 0, stream>>>(B, pose_kind, betas, pose, m, rotmats, nullptr, A, pf, posed, feat_hi, feat_lo);
+    (void)G;
     DANET_LAUNCH_CHECK();
     int nb = bodies_per_cta;
     if (nb <= 0) nb = B >= 32 ? 8 : (B >= 4 ? 4 : (B >= 2 ? 2 : 1));      // 8 is the measured optimum on B200 (tools/lbs_sweep.py)
@@ -722,6 +868,49 @@ extern "C" int danet_smpl_forward(danet_smpl_t h, int32_t B, const float* betas,
                                                                     smpl_joints, joints_h36m);
         DANET_LAUNCH_CHECK();
     }
+    return 0;
+}
+
+extern "C" int64_t danet_smpl_backward_workspace_bytes(danet_smpl_t h, int32_t B) {
+    if (!h || B <= 0) return 0;
+    int64_t cur = 0;
+    ws_off(cur, (int64_t)B * kJ * 12 * 4);          // G
+    ws_off(cur, (int64_t)B * kJ * 12 * 4);          // A
+    ws_off(cur, (int64_t)B * kPF * 4);              // pose feature
+    ws_off(cur, (int64_t)B * kJ * 3 * 4);           // posed joints
+    ws_off(cur, (int64_t)B * h->v.npad * 4);        // dL/dv_posed
+    ws_off(cur, (int64_t)B * kJ * 12 * 4);          // dL/dA
+    ws_off(cur, (int64_t)B * kPF * 4);              // dL/dpose_feature
+    return cur;
+}
+
+extern "C" int danet_smpl_backward(danet_smpl_t h, int32_t B, const float* betas, const float* rotmats,
+                                   const float* grad_verts, const float* grad_smpl_joints, float* grad_betas,
+                                   float* grad_rotmats, void* workspace, danet_stream_t stream_) {
+    DANET_CHECK(h, "danet_smpl_backward: null handle");
+    DANET_CHECK(B > 0, "danet_smpl_backward: empty batch (B=%d)", B);
+    DANET_CHECK(betas && rotmats && grad_verts && grad_betas && grad_rotmats && workspace, "danet_smpl_backward: null pointer");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const SmplView& m = h->v;
+    char* ws = (char*)workspace;
+    int64_t cur = 0;
+    float* G = (float*)(ws + ws_off(cur, (int64_t)B * kJ * 12 * 4));
+    float* A = (float*)(ws + ws_off(cur, (int64_t)B * kJ * 12 * 4));
+    float* pf = (float*)(ws + ws_off(cur, (int64_t)B * kPF * 4));
+    float* posed = (float*)(ws + ws_off(cur, (int64_t)B * kJ * 3 * 4));
+    float* dvp = (float*)(ws + ws_off(cur, (int64_t)B * m.npad * 4));
+    float* dA = (float*)(ws + ws_off(cur, (int64_t)B * kJ * 12 * 4));
+    float* dpf = (float*)(ws + ws_off(cur, (int64_t)B * kPF * 4));
+    DANET_CUDA(cudaMemsetAsync(dA, 0, (size_t)B * kJ * 12 * 4, stream));
+    k_smpl_pose<<<cdiv(B, 32), 32, 0, stream>>>(B, DANET_POSE_ROTMAT, betas, rotmats, m, nullptr, G, A, pf, posed, nullptr, nullptr);
+    DANET_LAUNCH_CHECK();
+    k_lbs_bwd_verts<<<dim3(m.ntiles, B), kTileV, 0, stream>>>(B, betas, pf, A, m, grad_verts, dvp, dA);
+    DANET_LAUNCH_CHECK();
+    const int nrow = 207 + m.nbetas;
+    k_lbs_bwd_blend<<<cdiv((int64_t)B * nrow * 32, 256), 256, 0, stream>>>(B, m, dvp, dpf, grad_betas);
+    DANET_LAUNCH_CHECK();
+    k_lbs_bwd_chain<<<cdiv(B, 32), 32, 0, stream>>>(B, m, betas, rotmats, G, dA, dpf, grad_smpl_joints, grad_betas, grad_rotmats);
+    DANET_LAUNCH_CHECK();
     return 0;
 }
 

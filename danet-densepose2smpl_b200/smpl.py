@@ -285,6 +285,27 @@ class SMPL(nn.Module):
                                 joints_J19=joints_J19, smpl_joints=smpl_joints, betas=betas,
                                 full_pose=full_pose)
 
+    @torch.no_grad()
+    def backward_lbs(self, betas, rotmats, grad_vertices, grad_smpl_joints=None):
+        """dL/dbetas [B,10], dL/drotmats [B,24,3,3] from dL/dvertices [B,6890,3] (and dL/dsmpl_joints [B,24,3]) -- the
+        SMPL-layer part of the reference's training back-propagation (train/trainer.py:148-215), for the rot-mat
+        input mode.  Gradients w.r.t. vertex-regressed joints enter through grad_vertices (J_regressor^T g)."""
+        _lib.require_cuda(betas, "betas")
+        dev = betas.device
+        B = betas.shape[0]
+        f = lambda t: t.detach().to(dev, torch.float32).contiguous()
+        betas, R, gv = f(betas), f(rotmats).reshape(B, 24, 3, 3), f(grad_vertices)
+        gj = f(grad_smpl_joints) if grad_smpl_joints is not None else None
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            h = self._handle(dev)
+            ws = torch.empty(int(lib.danet_smpl_backward_workspace_bytes(h, B)), dtype=torch.uint8, device=dev)
+            gb = torch.empty(B, betas.shape[1], device=dev)
+            gR = torch.empty(B, 24, 3, 3, device=dev)
+            _lib.check(lib.danet_smpl_backward(h, B, _lib.ptr(betas), _lib.ptr(R), _lib.ptr(gv), _lib.ptr(gj), _lib.ptr(gb),
+                                               _lib.ptr(gR), _lib.ptr(ws), _lib.stream_ptr(dev)), "smpl_backward")
+        return gb, gR
+
     def joints_h36m(self):
         """[B,17,3] J_regressor_h36m joints of the last forward (eval.py:186,202 fused into the pass)."""
         return self.last_joints_h36m

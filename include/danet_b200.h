@@ -70,6 +70,17 @@ int danet_smpl_forward(danet_smpl_t h, int32_t B, const float* betas, const floa
                        float* joints_h36m, float* rotmats, void* workspace,
                        int32_t bodies_per_cta, danet_stream_t stream);
 
+/* Backward of the SMPL layer -- the first piece of the training step (train/trainer.py:148-215 back-propagates
+ * vertex / joint losses through models/smpl.py:27-46 into the regressed betas and rotation matrices,
+ * models/danet/smpl_regressor.py:131-221).  rotmats [B,24,3,3] are the matrices the forward consumed (pose2rot=False,
+ * treated as free 3x3 inputs); grad_verts [B,V,3]; grad_smpl_joints [B,24,3] or NULL (gradients w.r.t. the regressed
+ * joints are folded into grad_verts by the caller: J_regressor^T g); outputs grad_betas [B,num_betas],
+ * grad_rotmats [B,24,3,3].  Recomputes the forward intermediates; fp32. */
+int64_t danet_smpl_backward_workspace_bytes(danet_smpl_t h, int32_t B);
+int danet_smpl_backward(danet_smpl_t h, int32_t B, const float* betas, const float* rotmats,
+                        const float* grad_verts, const float* grad_smpl_joints, float* grad_betas,
+                        float* grad_rotmats, void* workspace, danet_stream_t stream);
+
 /* utils/geometry.py:47-61 rot6d_to_rotmat: x [n,6] (viewed [n,3,2]) -> R [n,3,3] */
 int danet_rot6d_to_rotmat(int32_t n, const float* x, float* R, danet_stream_t stream);
 /* utils/geometry.py:9-45 batch_rodrigues (quaternion route): aa [n,3] -> R [n,3,3];

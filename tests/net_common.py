@@ -37,7 +37,7 @@ def golden_path(width, B=2):
     return os.path.join(GOLD, "net_w%d.npz" % width if B == 2 else "net_w%d_b%d.npz" % (width, B))
 
 
-def check_against_golden(out, width, para_tol, kps_tol, margin_eps, min_agree=1.0, B=2):
+def check_against_golden(out, width, para_tol, kps_tol, margin_eps, min_agree=1.0, B=2, near_tie_ok=False):
     """Compares infer_net output with the reference-generated golden.  Integer decisions (argmax
     maps) must agree wherever the reference's own top-2 margin exceeds `margin_eps`."""
     g = np.load(golden_path(width, B))
@@ -50,6 +50,16 @@ def check_against_golden(out, width, para_tol, kps_tol, margin_eps, min_agree=1.
     res["para_err"] = float(np.abs(para - g["para"]).max())
     res["kps_err"] = float(np.abs(kps - g["stn_kps"]).max())
     idx = i.argmax(1)
+    if near_tie_ok:
+        # an image whose Index / part argmax differs from the reference's at a pixel where the REFERENCE's own top-2
+        # margin is below margin_eps took the other side of a near-tie: its `para` is not comparable at 1e-4
+        # (see check_batch_against_golden); such flips at larger margins still fail below
+        pidx_ = parts[:, :, 2].argmax(2)
+        dirty = (idx != g["index_argmax"]).reshape(idx.shape[0], -1).any(1)[:nd] | (pidx_ != g["part_argmax"]).reshape(nd, -1).any(1)
+        res["images_with_near_tie_flips"] = int(dirty.sum())
+        clean = ~dirty
+        assert clean.any(), "every image took a near-tie flip: nothing to compare"
+        res["para_err"] = float(np.abs(para[:nd][clean] - g["para"][:nd][clean]).max())
     safe = g["index_margin"].astype(np.float32) > margin_eps
     res["index_agree_safe"] = float((idx == g["index_argmax"])[safe].mean())
     res["index_agree_all"] = float((idx == g["index_argmax"]).mean())

@@ -84,6 +84,10 @@ TC_CASES = [c for c in CONV_CASES if c[3] % 8 == 0 and c[4] % 8 == 0] + [
     (2, 2, 2, 512, 512, 3, 1, 1, 1, 1),           # body_net layer4: 2x2 maps
     (2, 16, 8, 16, 16, 1, 1, 1, 0, 0),            # a single tile, a single K step
     (5, 13, 9, 24, 40, 3, 1, 1, 1, 1),            # ragged: nothing divides the tile sizes
+    (13, 7, 7, 64, 64, 3, 1, 1, 1, 1),            # small maps: several images share a tile (2 per tile, ragged batch)
+    (7, 4, 4, 64, 64, 3, 1, 1, 1, 1),             # 3 images per tile
+    (11, 2, 2, 32, 48, 3, 1, 1, 1, 1),            # 5 images per tile
+    (9, 4, 4, 32, 32, 1, 1, 1, 0, 0),             # 1x1 on 4x4 maps: 4 images per tile, no zero rows
 ]
 
 

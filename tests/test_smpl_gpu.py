@@ -124,3 +124,43 @@ def test_mpjpe_kernel(smpl_model):
     gt = rng.normal(0, 0.3, (9, 14, 3)).astype(np.float32)
     got = mpjpe_h36m(torch.from_numpy(j17).to(dev), torch.from_numpy(gt).to(dev)).cpu().numpy()
     np.testing.assert_allclose(got, lbs.mpjpe_h36m(j17.astype(np.float64), gt), atol=1e-6)
+
+
+def test_smpl_backward_matches_fp64_finite_differences(smpl_model):
+    """LBS backward (danet_smpl_backward): dL/dbetas and dL/dR for L = <w_v, vertices> + <w_j, smpl_joints> against
+    central finite differences of the fp64 oracle (oracle/lbs.py), every beta and every rotation-matrix entry."""
+    import danet_b200
+    dev = torch.device("cuda:0")
+    B = 2
+    rng = np.random.default_rng(42)
+    betas = rng.normal(0, 1, (B, 10))
+    x6 = rng.normal(0, 1, (B, 24, 6))
+    R = lbs.rot6d_to_rotmat(x6.reshape(-1, 6)).reshape(B, 24, 3, 3).astype(np.float64)
+    wv = rng.normal(0, 1, (B, 6890, 3))
+    wj = rng.normal(0, 1, (B, 24, 3))
+
+    def loss(be, Rm):
+        o = lbs.smpl_forward(smpl_model, be, Rm[:, 1:], Rm[:, :1], pose2rot=False, dtype=np.float64)
+        return (o["vertices"] * wv).sum() + (o["smpl_joints"] * wj).sum()
+    eps = 1e-5
+    gb_fd = np.zeros_like(betas)
+    for i in range(B):
+        for l in range(10):
+            bp, bm = betas.copy(), betas.copy()
+            bp[i, l] += eps; bm[i, l] -= eps
+            gb_fd[i, l] = (loss(bp, R) - loss(bm, R)) / (2 * eps)
+    gR_fd = np.zeros_like(R)
+    for i in range(B):
+        for j in range(24):
+            for e in range(9):
+                Rp, Rm_ = R.copy(), R.copy()
+                Rp[i, j].reshape(-1)[e] += eps; Rm_[i, j].reshape(-1)[e] -= eps
+                gR_fd[i, j].reshape(-1)[e] = (loss(betas, Rp) - loss(betas, Rm_)) / (2 * eps)
+    smpl = danet_b200.SMPL(smpl_model, batch_size=B).to(dev)
+    t = lambda a: torch.from_numpy(a.astype(np.float32)).to(dev)
+    gb, gR = smpl.backward_lbs(t(betas), t(R), t(wv), t(wj))
+    sb, sR = np.abs(gb_fd).max(), np.abs(gR_fd).max()
+    eb = np.abs(gb.cpu().numpy() - gb_fd).max() / sb
+    eR = np.abs(gR.cpu().numpy() - gR_fd).max() / sR
+    print("LBS backward vs fp64 finite differences: rel err dbeta %.2e dR %.2e" % (eb, eR))
+    assert eb < 2e-4 and eR < 2e-4

@@ -31,6 +31,11 @@ CASES = [
     (2, 14, 14, 64, 64, 3, 1, 1, 1, 1),
     (2, 28, 28, 64, 128, 3, 2, 1, 1, 0),
     (2, 28, 28, 64, 128, 1, 2, 1, 0, 0),
+    (13, 7, 7, 64, 64, 3, 1, 1, 1, 1),           # stacked small maps: 2 images per tile, ragged batch
+    (7, 4, 4, 64, 64, 3, 1, 1, 1, 1),            # 3 images per tile (rows of 5)
+    (11, 2, 2, 32, 48, 3, 1, 1, 1, 1),           # 5 images per tile
+    (9, 4, 4, 32, 32, 1, 1, 1, 0, 0),            # 1x1: no zero rows, 4 images per tile
+    (5, 5, 3, 16, 16, 3, 1, 1, 0, 1),            # rows of 6: 2 images per tile, narrow
 ]
 
 

@@ -872,24 +872,36 @@ static std::mutex g_tc_mu;
 static unsigned long long g_tc_devs = 0;
 static bool g_use_pdl = true;
 
-int conv_tc_group_launch(int n, const danet_conv_problem* probs, cudaStream_t stream) {
+// geometry of every problem + the shared-memory rings of the launch (sub-tile pairs are given up, largest halo first,
+// until the rings fit)
+static int configure_group(int n, const danet_conv_desc* const* descs, tc::ArgsN* a) {
     using namespace tc;
     DANET_CHECK(n >= 1 && n <= kMaxProb, "danet_conv_tc_group: 1..%d problems per launch (got %d)", kMaxProb, n);
-    ArgsN a;
-    memset(&a, 0, sizeof(a));
-    a.nprob = n;
+    memset(a, 0, sizeof(*a));
+    a->nprob = n;
     int S_req[kMaxProb];
     const int s_env = env_int("DANET_TC_S", 2);
     for (int i = 0; i < n; ++i) S_req[i] = s_env;
     for (int attempt = 0;; ++attempt) {
         for (int i = 0; i < n; ++i)
-            if (!make_prob(&probs[i].d, S_req[i], &a.p[i])) { set_error("danet_conv_tc_group: problem %d has an unsupported shape", i); return -1; }
-        if (plan_rings(&a)) break;
-        // shrink the problem with the largest halo stage to one sub-tile and retry
+            if (!make_prob(descs[i], S_req[i], &a->p[i])) { set_error("danet_conv_tc_group: problem %d has an unsupported shape", i); return -1; }
+        if (plan_rings(a)) break;
         int worst = -1, wb = 0;
-        for (int i = 0; i < n; ++i) if (a.p[i].S > 1 && max_stage_bytes(a.p[i]) > wb) { wb = max_stage_bytes(a.p[i]); worst = i; }
+        for (int i = 0; i < n; ++i) if (a->p[i].S > 1 && max_stage_bytes(a->p[i]) > wb) { wb = max_stage_bytes(a->p[i]); worst = i; }
         DANET_CHECK(worst >= 0 && attempt < 2 * kMaxProb, "danet_conv_tc_group: shared-memory plan does not fit");
         S_req[worst] = 1;
+    }
+    return 0;
+}
+
+int conv_tc_group_launch(int n, const danet_conv_problem* probs, cudaStream_t stream) {
+    using namespace tc;
+    ArgsN a;
+    {
+        const danet_conv_desc* dp[kMaxProb];
+        DANET_CHECK(n >= 1 && n <= kMaxProb, "danet_conv_tc_group: 1..%d problems per launch (got %d)", kMaxProb, n);
+        for (int i = 0; i < n; ++i) dp[i] = &probs[i].d;
+        if (configure_group(n, dp, &a) != 0) return -1;
     }
     // tiles are dealt round-robin over the persistent CTAs in problem order: the problems with the most expensive
     // tiles go first, so that the long tiles start early and the cheap ones fill the tail
@@ -1007,6 +1019,21 @@ extern "C" int danet_conv_tc_pack(const danet_conv_desc* d, const float* w_simt,
     tc::k_pack<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g, w_simt, (__half*)((uint8_t*)w_packed + tc::kPackHeader), scale);
     DANET_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int danet_conv_tc_config(int32_t n, const danet_conv_desc* descs, int32_t* subtiles, int32_t* stages) {
+    DANET_CHECK(descs && subtiles && stages, "danet_conv_tc_config: null pointer");
+    const danet_conv_desc* dp[tc::kMaxProb];
+    DANET_CHECK(n >= 1 && n <= tc::kMaxProb, "danet_conv_tc_config: 1..%d problems (got %d)", tc::kMaxProb, n);
+    for (int i = 0; i < n; ++i) dp[i] = &descs[i];
+    tc::ArgsN* a = new tc::ArgsN();
+    const int rc = configure_group(n, dp, a);
+    if (rc == 0) {
+        for (int i = 0; i < n; ++i) subtiles[i] = a->p[i].S;
+        stages[0] = a->na_stages; stages[1] = a->nb_stages;
+    }
+    delete a;
+    return rc;
 }
 
 extern "C" int danet_conv_tc_group(int32_t n, const danet_conv_problem* probs, danet_stream_t stream) {

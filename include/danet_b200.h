@@ -173,6 +173,10 @@ typedef struct {
     const float* bias;                 /* [wsets][Cout] or NULL */
 } danet_conv_problem;
 int danet_conv_tc_group(int32_t n, const danet_conv_problem* problems, danet_stream_t stream);
+/* The launch configuration a group of n problems would get: sub-tiles per pipeline step (1 or 2) of every problem and
+ * the depth of the shared activation / weight rings (stages[0], stages[1]).  The rings are sized for the largest
+ * member, so a host may use this to keep a dominant problem from losing its sub-tile pair to a small companion. */
+int danet_conv_tc_config(int32_t n, const danet_conv_desc* descs, int32_t* subtiles, int32_t* stages);
 /* bytes / packing helper: converts the SIMT layout above into the swizzled shared-memory image blocks of
  * split-fp16 weights the tcgen05 kernel bulk-copies (device -> device, once at load). */
 int64_t danet_conv_tc_packed_bytes(const danet_conv_desc* d);

@@ -1,30 +1,40 @@
-"""Summarises an `ncu --metrics gpu__time_duration.sum --csv` launch list per kernel (count, total, share)."""
-import collections, csv, sys
+"""Condense `ncu --page raw --csv` output to the metrics the roofline discussion uses.
+python tools/ncu_summary.py <report.ncu-rep> [kernel regex]"""
+import csv
+import io
+import re
+import subprocess
+import sys
 
-def main(path, out=None):
-    lines = [l for l in open(path) if not l.startswith("==")]
-    agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
-    for row in csv.DictReader(lines):
-        name = row["Kernel Name"].split("(")[0]
-        if row.get("Metric Name", "gpu__time_duration.sum") != "gpu__time_duration.sum":
+KEYS = ["gpu__time_duration.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.sum",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+        "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum",
+        "l1tex__data_pipe_lsu_wavefronts.sum", "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_membar_per_issue_active.ratio", "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "smsp__average_warps_issue_stalled_sleeping_per_issue_active.ratio"]
+
+
+def main():
+    rep = sys.argv[1]
+    pat = re.compile(sys.argv[2]) if len(sys.argv) > 2 else None
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr = rows[0]
+    col = {h: i for i, h in enumerate(hdr)}
+    units = rows[1]
+    for r in rows[2:]:
+        name = r[col["Kernel Name"]]
+        if pat and not pat.search(name):
             continue
-        try:
-            v = float(row["Metric Value"].replace(",", ""))
-        except ValueError:
-            continue
-        u = row["Metric Unit"]
-        v = v / 1e3 if u == "ns" else v * 1e3 if u == "ms" else v * 1e6 if u in ("s", "second") else v
-        a = agg[name]; a[0] += 1; a[1] += v; a[2] = max(a[2], v)
-    tot = sum(v[1] for v in agg.values())
-    txt = ["# per-kernel device time from %s (cold-cache, serialised: compare SHARES)" % path,
-           "%-64s %6s %12s %10s %7s" % ("kernel", "n", "total_us", "max_us", "share")]
-    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        txt.append("%-64s %6d %12.1f %10.1f %6.2f%%" % (k[:64], v[0], v[1], v[2], 100 * v[1] / tot))
-    txt.append("total_us %.1f" % tot)
-    s = "\n".join(txt) + "\n"
-    if out:
-        open(out, "w").write(s)
-    print(s)
+        print("== %s  grid %s block %s" % (name[:60], r[col.get("Grid Size", 0)], r[col.get("Block Size", 0)]))
+        for k in KEYS:
+            if k in col:
+                print("   %-90s %s %s" % (k, r[col[k]], units[col[k]]))
+
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else None)
+    main()

@@ -159,7 +159,7 @@ static bool make_prob(const danet_conv_desc* d, int S_req, Prob* g) {
     g->rows_blk = g->NT * (g->nconcat ? 2 : 1);
     g->tap_bytes = g->rows_blk * swb;
     int tg = max_ntap;
-    while (tg > 1 && tg * g->tap_bytes > 24 * 1024) --tg;
+    while (tg > 1 && tg * g->tap_bytes > env_int("DANET_TC_TGKB", 24) * 1024) --tg;
     g->TG = tg;
     g->b_block_bytes = (tg * g->tap_bytes + 1023) / 1024 * 1024;
     g->bpc = 0;
@@ -223,7 +223,7 @@ static bool plan_rings(ArgsN* a) {
     }
     a->a_slot_bytes = (amax + 1023) / 1024 * 1024;
     a->b_slot_bytes = (bmax + 1023) / 1024 * 1024;
-    int nb = 3;
+    int nb = env_int("DANET_TC_NB", 3);
     int na = (kSmemMax - kSmemFixed - nb * a->b_slot_bytes) / a->a_slot_bytes;
     if (na < need_a) { nb = 2; na = (kSmemMax - kSmemFixed - nb * a->b_slot_bytes) / a->a_slot_bytes; }
     if (na < (need_a == 4 ? 2 : 2)) return false;

@@ -181,11 +181,11 @@ class SMPL(nn.Module):
         """The device-side model (danet_smpl_t) snapshots the buffers: drop it whenever they may have changed."""
         try:
             lib = _lib.load()
-            for h in self._handles.values():
+            for h in self.__dict__.get("_handles", {}).values():
                 lib.danet_smpl_destroy(h)
         except Exception:
             pass
-        self._handles = {}
+        self.__dict__["_handles"] = {}                  # plain attribute: safe during interpreter shutdown too
 
     def __del__(self):
         self._drop_handles()

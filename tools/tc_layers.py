@@ -57,15 +57,22 @@ def time_layer(case, exact, iters=10):
     return us, flop / us / 1e6
 
 
+MODES = (0, 1)
+
 if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else ""
+    if len(sys.argv) > 2:
+        MODES = (1,) if sys.argv[2] == "exact" else (0,)
     tot = {0: 0.0, 1: 0.0}
     print("# %s S=%s variant=%s" % (tag, os.environ.get("DANET_TC_S", "2"), os.environ.get("DANET_TC_VARIANT", "0")))
     for case, cnt in LAYERS:
         row = []
-        for exact in (0, 1):
+        for exact in MODES:
             us, tf = time_layer(case, bool(exact))
             tot[exact] += us * cnt
             row.append("%8.1f us %6.1f TF" % (us, tf))
-        print("%-46s x%-2d fast %s | exact %s" % (case, cnt, row[0], row[1]), flush=True)
+        if len(MODES) == 2:
+            print("%-46s x%-2d fast %s | exact %s" % (case, cnt, row[0], row[1]), flush=True)
+        else:
+            print("%-46s x%-2d %s %s" % (case, cnt, "exact" if MODES[0] else "fast", row[0]), flush=True)
     print("weighted ms: fast %.2f exact %.2f" % (tot[0] / 1e3, tot[1] / 1e3))

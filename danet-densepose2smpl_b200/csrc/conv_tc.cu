@@ -82,6 +82,7 @@ constexpr int kMaxProb = 6;
 struct ArgsN {
     int nprob, total_tiles, na_stages, a_slot_bytes, nb_stages, b_slot_bytes;
     int variant, pad_;                   // bring-up knock-outs (DANET_TC_VARIANT): 1 no stores, 2 no residual/bias loads, 4 no MMAs
+    long long* prof;                     // bring-up: per-role wait cycles of CTA 0 (danet_conv_tc_set_profile_buffer), else NULL
     unsigned* sched;                     // [2]: dynamic tile counter, finished-CTA counter (self-resetting); NULL = static round-robin
     Prob p[kMaxProb];
 };
@@ -159,7 +160,9 @@ static bool make_prob(const danet_conv_desc* d, int S_req, Prob* g) {
     g->rows_blk = g->NT * (g->nconcat ? 2 : 1);
     g->tap_bytes = g->rows_blk * swb;
     int tg = max_ntap;
-    while (tg > 1 && tg * g->tap_bytes > env_int("DANET_TC_TGKB", 24) * 1024) --tg;
+    // weight block size: larger blocks mean fewer barrier round trips (fast mode: +7 %, measured); exact mode keeps two
+    // more ring slots instead
+    while (tg > 1 && tg * g->tap_bytes > env_int("DANET_TC_TGKB", g->exact ? 24 : 48) * 1024) --tg;
     g->TG = tg;
     g->b_block_bytes = (tg * g->tap_bytes + 1023) / 1024 * 1024;
     g->bpc = 0;
@@ -185,7 +188,7 @@ static bool make_prob(const danet_conv_desc* d, int S_req, Prob* g) {
     {
         const int gph0 = (g->NT / 16 + 1) / 2;
         if (g->exact && !g->big && g->S * gph0 <= 4) {
-            g->lseg = env_int("DANET_TC_LSEG", 8);
+            g->lseg = env_int("DANET_TC_LSEG", 16);
             int cnt = 0, nseg = 0;
             for (int c = 0; c < g->nchunks; ++c) {
                 const int kreal = (d->Cin - c * g->KCH + 15) / 16, kmma = g->KCH / 16;
@@ -259,6 +262,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (done) return;
     }
     __trap();                                        // bounded wait: never hang the device
+}
+// bring-up instrumentation: a wait that adds its duration to *acc when profiling is on
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, bool on, long long* acc) {
+    if (!on) { mbar_wait(bar, parity); return; }
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    *acc += clock64() - t0;
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -392,6 +402,8 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
         if (lane == 0) {
             int as = 0; uint32_t aph = 0;
             int pi = 0;
+            const bool pon = a.prof != nullptr && blockIdx.x == 0;
+            long long pw = 0; const long long pt0 = clock64();
             // Tile scheduler: this thread publishes tile indices kSchedAhead tiles ahead of its own loads, so that the
             // weight producer can prefetch for the coming tiles while the MMAs work on the current one.  The first
             // kSchedStatic tiles of a CTA are its round-robin share (no atomic latency at start-up), later ones come
@@ -421,7 +433,7 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
                 for (int c = 0; c < P.nchunks; ++c)
                     for (int slot = 0; slot < P.npa; ++slot)
                         for (int pl = 0; pl <= P.exact; ++pl) {
-                            mbar_wait(bar_a_empty + 8 * as, ((aph >> as) & 1u) ^ 1u);
+                            mbar_wait_t(bar_a_empty + 8 * as, ((aph >> as) & 1u) ^ 1u, pon, &pw);
                             if (P.nstack > 1) {
                                 const uint32_t box_bytes = (uint32_t)(P.box_h * P.sbo_a[slot]);
                                 mbar_expect_tx(bar_a_full + 8 * as, box_bytes * P.nstack);
@@ -437,14 +449,19 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
                             if (++as == a.na_stages) as = 0;
                         }
             }
+            if (pon) { a.prof[0] = clock64() - pt0; a.prof[1] = pw; }
         }
     } else if (warp == kWarpB) {
         // ================= B producer: bulk copies of pre-packed weight blocks =================
         if (lane == 0) {
             int bs = 0; uint32_t bph = 0;
             int pi = 0;
+            const bool pon = a.prof != nullptr && blockIdx.x == 0;
+            long long pw = 0, ps = 0; const long long pt0 = clock64();
             for (int seq = 0;; ++seq) {
+                const long long ts0 = pon ? clock64() : 0;
                 const int tile = sched_next(bar_sched_full, bar_sched_empty, sched_ring, seq);
+                if (pon) ps += clock64() - ts0;
                 if (tile >= a.total_tiles) break;
                 pi = 0;
                 while (tile >= a.p[pi].tile_base + a.p[pi].tile_count) ++pi;
@@ -453,13 +470,14 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
                 const int ws = tc.img - mdiv(tc.img, P.m_ws) * P.wsets;
                 const uint8_t* src = P.wpk + kPackHeader + ((long long)ws * P.blocks_per_set + (long long)tc.nt * P.nblk) * P.b_block_bytes;
                 for (int b = 0; b < P.nblk; ++b) {
-                    mbar_wait(bar_b_empty + 8 * bs, ((bph >> bs) & 1u) ^ 1u);
+                    mbar_wait_t(bar_b_empty + 8 * bs, ((bph >> bs) & 1u) ^ 1u, pon, &pw);
                     mbar_expect_tx(bar_b_full + 8 * bs, (uint32_t)P.b_block_bytes);
                     bulk_g2s(sB + bs * a.b_slot_bytes, src + (long long)b * P.b_block_bytes, (uint32_t)P.b_block_bytes, bar_b_full + 8 * bs);
                     bph ^= 1u << bs;
                     if (++bs == a.nb_stages) bs = 0;
                 }
             }
+            if (pon) { a.prof[2] = clock64() - pt0; a.prof[3] = pw; a.prof[4] = ps; }
         }
     } else if (warp == kWarpMma) {
         // ================= MMA issuer =================
@@ -467,10 +485,14 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
         // elected lane issues the tcgen05 instructions.
         int as = 0, bs = 0; uint32_t aph = 0, bph = 0, eph = 0; int tog = 0;
         int pi = 0;
+        const bool pon = a.prof != nullptr && blockIdx.x == 0;
+        long long pwa = 0, pwb = 0, pwe = 0, pws = 0; const long long pt0 = clock64();
         for (int seq = 0;; ++seq) {
             int tile = 0;
+            const long long ts0 = pon ? clock64() : 0;
             if (lane == 0) tile = sched_next(bar_sched_full, bar_sched_empty, sched_ring, seq);
             tile = __shfl_sync(0xffffffffu, tile, 0);
+            if (pon) pws += clock64() - ts0;
             if (tile >= a.total_tiles) break;
             pi = 0;
             while (tile >= a.p[pi].tile_base + a.p[pi].tile_count) ++pi;
@@ -496,12 +518,12 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
                 const int kv = kreal < kmma ? kreal : kmma;       // K steps wholly beyond Cin are not issued
                 for (int slot = 0; slot < npa; ++slot) {
                     const int as_hi = as;
-                    mbar_wait(bar_a_full + 8 * as, (aph >> as) & 1u);
+                    mbar_wait_t(bar_a_full + 8 * as, (aph >> as) & 1u, pon, &pwa);
                     aph ^= 1u << as; if (++as == a.na_stages) as = 0;
                     int as_lo = as_hi;
                     if (exact) {
                         as_lo = as;
-                        mbar_wait(bar_a_full + 8 * as, (aph >> as) & 1u);
+                        mbar_wait_t(bar_a_full + 8 * as, (aph >> as) & 1u, pon, &pwa);
                         aph ^= 1u << as; if (++as == a.na_stages) as = 0;
                     }
                     tc_fence_after();
@@ -514,18 +536,18 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
                         const int ntk = min(TG, ntap - k0);
                         if (need_acc) {
                             if (big) {
-                                mbar_wait(bar_acc_empty, (eph & 1u) ^ 1u); mbar_wait(bar_acc_empty + 8, ((eph >> 1) & 1u) ^ 1u);
+                                mbar_wait_t(bar_acc_empty, (eph & 1u) ^ 1u, pon, &pwe); mbar_wait_t(bar_acc_empty + 8, ((eph >> 1) & 1u) ^ 1u, pon, &pwe);
                                 eph ^= 3u; cs = 0;
                             } else {
                                 cs = tog; tog ^= 1;
-                                mbar_wait(bar_acc_empty + 8 * cs, ((eph >> cs) & 1u) ^ 1u);
+                                mbar_wait_t(bar_acc_empty + 8 * cs, ((eph >> cs) & 1u) ^ 1u, pon, &pwe);
                                 eph ^= 1u << cs;
                             }
                             tc_fence_after();
                             d_base = tmem_base + cs * 256;
                             acc = 0; need_acc = false; seg_cnt = 0;
                         }
-                        mbar_wait(bar_b_full + 8 * bs, (bph >> bs) & 1u);
+                        mbar_wait_t(bar_b_full + 8 * bs, (bph >> bs) & 1u, pon, &pwb);
                         tc_fence_after();
                         const uint64_t bd = bd0 + ((sB + bs * a.b_slot_bytes) >> 4);
                         if (elect_one()) {
@@ -569,6 +591,7 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
                 }
             }
         }
+        if (pon && lane == 0) { a.prof[5] = clock64() - pt0; a.prof[6] = pwa; a.prof[7] = pwb; a.prof[8] = pwe; a.prof[9] = pws; }
     } else {
         // ================= epilogue: TMEM -> (+ bias, residual) -> ReLU -> global =================
         // Row-per-thread mapping (tcgen05.ld 32x32b.x16): lane i of a warp owns TMEM lane 32q+i = output pixel
@@ -585,11 +608,15 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
         uint32_t fph = 0; int tog = 0;
         int pi = 0;
         const bool do_store = !(a.variant & 1);
+        const bool pon = a.prof != nullptr && blockIdx.x == 0 && warp == 0 && lane == 0;
+        long long pwf = 0, pws = 0, pinit = 0, pseg = 0, pst = 0; const long long pt0 = clock64();
         pdl_wait();                                              // residual reads / output writes
         for (int seq = 0;; ++seq) {
             int tile = 0;
+            const long long ts0 = pon ? clock64() : 0;
             if (lane == 0) tile = sched_next(bar_sched_full, bar_sched_empty, sched_ring, seq);
             tile = __shfl_sync(0xffffffffu, tile, 0);
+            if (pon) pws += clock64() - ts0;
             if (tile >= a.total_tiles) break;
             pi = 0;
             while (tile >= a.p[pi].tile_base + a.p[pi].tile_count) ++pi;
@@ -623,6 +650,7 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
             const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
             int cs_first = 0;
             for (int u0 = 0; u0 < (nunits > 0 ? nunits : 1); u0 += 4) {
+                const long long ti0 = pon ? clock64() : 0;
                 float acc[4][16];
                 uint32_t eoff[4]; int cou[4]; bool okp[4];
 #pragma unroll
@@ -633,7 +661,7 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
                     cou[uu] = grp * 16;
                     okp[uu] = u < nunits && row_ok && ow < Wo;
                     eoff[uu] = (rowbase + ow) * Cout + tc.nt * NT + grp * 16;
-                    // accumulator <- bias (+ residual)
+                    // accumulator <- bias
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int co = grp * 16 + 8 * h;
@@ -642,34 +670,67 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
                         if (bias && ch_ok) { b0 = __ldg(reinterpret_cast<const float4*>(bias + boff + co)); b1 = __ldg(reinterpret_cast<const float4*>(bias + boff + co + 4)); }
                         float* ac = &acc[uu][8 * h];
                         ac[0] = b0.x; ac[1] = b0.y; ac[2] = b0.z; ac[3] = b0.w; ac[4] = b1.x; ac[5] = b1.y; ac[6] = b1.z; ac[7] = b1.w;
-                        if (okp[uu] && ch_ok) {
-                            if (res_f) {
-                                const float4 r0 = __ldg(reinterpret_cast<const float4*>(res_f + eoff[uu] + 8 * h));
-                                const float4 r1 = __ldg(reinterpret_cast<const float4*>(res_f + eoff[uu] + 8 * h + 4));
-                                ac[0] += r0.x; ac[1] += r0.y; ac[2] += r0.z; ac[3] += r0.w; ac[4] += r1.x; ac[5] += r1.y; ac[6] += r1.z; ac[7] += r1.w;
-                            } else if (res_hi) {
-                                const uint4 rh = __ldg(reinterpret_cast<const uint4*>(res_hi + eoff[uu] + 8 * h));
-                                float2 t;
-                                t = h2_to_f2(rh.x); ac[0] += t.x; ac[1] += t.y; t = h2_to_f2(rh.y); ac[2] += t.x; ac[3] += t.y;
-                                t = h2_to_f2(rh.z); ac[4] += t.x; ac[5] += t.y; t = h2_to_f2(rh.w); ac[6] += t.x; ac[7] += t.y;
-                                if (res_lo) {
-                                    const uint4 rl = __ldg(reinterpret_cast<const uint4*>(res_lo + eoff[uu] + 8 * h));
-                                    t = h2_to_f2(rl.x); ac[0] += t.x; ac[1] += t.y; t = h2_to_f2(rl.y); ac[2] += t.x; ac[3] += t.y;
-                                    t = h2_to_f2(rl.z); ac[4] += t.x; ac[5] += t.y; t = h2_to_f2(rl.w); ac[6] += t.x; ac[7] += t.y;
-                                }
-                            }
-                        }
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) ac[j] *= wsc.x;
                     }
                 }
+                // + residual: all the 16-byte loads of one plane are issued back to back (8 in flight per lane) before the
+                // first use -- one memory round trip per plane instead of one per load (measured: the per-load form cost
+                // 6K cycles per tile and made the MMA warp wait for accumulator stages)
+                if (res_f) {
+#pragma unroll
+                    for (int hp = 0; hp < 2; ++hp) {                  // two passes of 4 x 16 bytes per unit half
+                        float4 r[4][2];
+#pragma unroll
+                        for (int uu = 0; uu < 4; ++uu)
+#pragma unroll
+                            for (int k = 0; k < 2; ++k) {
+                                r[uu][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (okp[uu] && cou[uu] + 8 * hp < cw) r[uu][k] = __ldg(reinterpret_cast<const float4*>(res_f + eoff[uu] + 8 * hp + 4 * k));
+                            }
+#pragma unroll
+                        for (int uu = 0; uu < 4; ++uu) {
+                            float* ac = &acc[uu][8 * hp];
+                            ac[0] += r[uu][0].x; ac[1] += r[uu][0].y; ac[2] += r[uu][0].z; ac[3] += r[uu][0].w;
+                            ac[4] += r[uu][1].x; ac[5] += r[uu][1].y; ac[6] += r[uu][1].z; ac[7] += r[uu][1].w;
+                        }
+                    }
+                } else if (res_hi) {
+#pragma unroll
+                    for (int pl = 0; pl < 2; ++pl) {
+                        const __half* __restrict__ rp = pl == 0 ? res_hi : res_lo;
+                        if (rp == nullptr) break;
+                        uint4 r[4][2];
+#pragma unroll
+                        for (int uu = 0; uu < 4; ++uu)
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                r[uu][h] = make_uint4(0u, 0u, 0u, 0u);
+                                if (okp[uu] && cou[uu] + 8 * h < cw) r[uu][h] = __ldg(reinterpret_cast<const uint4*>(rp + eoff[uu] + 8 * h));
+                            }
+#pragma unroll
+                        for (int uu = 0; uu < 4; ++uu)
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                float* ac = &acc[uu][8 * h];
+                                float2 t;
+                                t = h2_to_f2(r[uu][h].x); ac[0] += t.x; ac[1] += t.y; t = h2_to_f2(r[uu][h].y); ac[2] += t.x; ac[3] += t.y;
+                                t = h2_to_f2(r[uu][h].z); ac[4] += t.x; ac[5] += t.y; t = h2_to_f2(r[uu][h].w); ac[6] += t.x; ac[7] += t.y;
+                            }
+                    }
+                }
+#pragma unroll
+                for (int uu = 0; uu < 4; ++uu)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[uu][j] *= wsc.x;
+                if (pon) pinit += clock64() - ti0;
                 // add every K segment of the tile from TMEM (a multi-batch tile has a single segment)
                 for (int seg = 0; seg < nseg; ++seg) {
+                    const long long tg0 = pon ? clock64() : 0;
+                    long long wseg = 0;
                     int cs = cs_first;
                     if (u0 == 0) {
                         cs = 0;
                         if (!big) { cs = tog; tog ^= 1; }
-                        mbar_wait(bar_acc_full + 8 * cs, (fph >> cs) & 1u);
+                        mbar_wait_t(bar_acc_full + 8 * cs, (fph >> cs) & 1u, pon, &wseg);
                         fph ^= 1u << cs;
                         tc_fence_after();
                         cs_first = cs;
@@ -703,7 +764,9 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
                         if (big) { mbar_arrive(bar_acc_empty); mbar_arrive(bar_acc_empty + 8); }
                         else mbar_arrive(bar_acc_empty + 8 * cs);
                     }
+                    if (pon) { pwf += wseg; pseg += clock64() - tg0 - wseg; }
                 }
+                const long long tst0 = pon ? clock64() : 0;
                 // ReLU, split, store
 #pragma unroll
                 for (int uu = 0; uu < 4; ++uu) {
@@ -739,8 +802,10 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
                         }
                     }
                 }
+                if (pon) pst += clock64() - tst0;
             }
         }
+        if (pon) { a.prof[10] = clock64() - pt0; a.prof[11] = pwf; a.prof[12] = pws; a.prof[13] = pinit; a.prof[14] = pseg; a.prof[15] = pst; }
     }
     tc_fence_before();
     __syncthreads();
@@ -864,6 +929,7 @@ static int encode_x(const Prob& g, const void* base, CUtensorMap* tm) {
 
 }  // namespace tc
 
+static long long* g_tc_prof = nullptr;
 static int g_sm_count[64];
 static unsigned* g_sched[64];              // per device: kSchedSlots x {tile counter, done counter}, zero-initialised, self-resetting
 static unsigned g_sched_seq[64];
@@ -939,6 +1005,7 @@ int conv_tc_group_launch(int n, const danet_conv_problem* probs, cudaStream_t st
     }
     a.total_tiles = base;
     a.variant = env_int("DANET_TC_VARIANT", 0);
+    a.prof = g_tc_prof;
     int dev = 0;
     DANET_CUDA(cudaGetDevice(&dev));
     DANET_CHECK(dev >= 0 && dev < 64, "conv_tc: device ordinal %d out of range", dev);
@@ -973,6 +1040,12 @@ int conv_tc_group_launch(int n, const danet_conv_problem* probs, cudaStream_t st
 }  // namespace danet
 
 using namespace danet;
+
+// bring-up instrumentation: device buffer of 16 int64 written by CTA 0 of every following launch (NULL = off):
+// [0] A-producer total, [1] its a_empty waits; [2] B-producer total, [3] b_empty waits, [4] scheduler waits;
+// [5] MMA warp total, [6] a_full, [7] b_full, [8] acc_empty, [9] scheduler waits;
+// [10] epilogue warp 0 total, [11] acc_full waits, [12] scheduler waits, [13] bias/residual init, [14] TMEM segments, [15] stores
+extern "C" int danet_conv_tc_set_profile_buffer(void* dev_buf) { g_tc_prof = (long long*)dev_buf; return 0; }
 
 extern "C" int danet_conv_tc_supported(const danet_conv_desc* d) {
     tc::Prob g;

@@ -182,6 +182,9 @@ int danet_conv_tc_config(int32_t n, const danet_conv_desc* descs, int32_t* subti
 int64_t danet_conv_tc_packed_bytes(const danet_conv_desc* d);
 int danet_conv_tc_pack(const danet_conv_desc* d, const float* w_simt, void* w_packed, danet_stream_t stream);
 int danet_conv_tc_supported(const danet_conv_desc* d);
+/* bring-up instrumentation: 16 x int64 device buffer receiving per-role cycle counters of CTA 0 of
+ * every following tensor-core launch (NULL = off; layout in csrc/conv_tc.cu) */
+int danet_conv_tc_set_profile_buffer(void* dev_buf);
 /* fp32 -> split-fp16 planes (lo may be NULL) and back (lo may be NULL); n elements */
 int danet_act_split(int64_t n, const float* x, void* hi, void* lo, danet_stream_t stream);
 int danet_act_merge(int64_t n, const void* hi, const void* lo, float* y, danet_stream_t stream);

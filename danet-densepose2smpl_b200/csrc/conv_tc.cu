@@ -106,7 +106,7 @@ static bool make_prob(const danet_conv_desc* d, int S_req, Prob* g) {
     // exact mode: N tiles of <= 128 channels, so that the hi and lo weight rows of a tap form ONE operand of 2*NT <= 256
     // rows (hi*[hi|lo] is one MMA) and the small terms get their own accumulator columns [NT, 2*NT)
     const int np = (d->Cout + 15) / 16 * 16;
-    const int ntmax = g->exact ? 128 : 256;
+    const int ntmax = env_int(g->exact ? "DANET_TC_NTMAX_EXACT" : "DANET_TC_NTMAX_FAST", g->exact ? 128 : 256);
     g->ntn = (np + ntmax - 1) / ntmax;
     g->NT = ((np + g->ntn - 1) / g->ntn + 15) / 16 * 16;
     g->nconcat = g->exact;
@@ -188,7 +188,7 @@ static bool make_prob(const danet_conv_desc* d, int S_req, Prob* g) {
     {
         const int gph0 = (g->NT / 16 + 1) / 2;
         if (g->exact && !g->big && g->S * gph0 <= 4) {
-            g->lseg = env_int("DANET_TC_LSEG", 16);
+            g->lseg = env_int("DANET_TC_LSEG", 8);
             int cnt = 0, nseg = 0;
             for (int c = 0; c < g->nchunks; ++c) {
                 const int kreal = (d->Cin - c * g->KCH + 15) / 16, kmma = g->KCH / 16;

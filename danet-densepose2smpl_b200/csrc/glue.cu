@@ -38,6 +38,18 @@ __global__ void k_nchw_to_nhwc(int N, int C, int HW, int Cp, const float* __rest
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)N * HW) return;
     const int n = (int)(i / HW), p = (int)(i % HW);
+    if ((Cp & 3) == 0) {
+        // 16-byte (fp32) / 8-byte (fp16 planes) stores per 4 channels; reads are coalesced across pixels
+        for (int c = 0; c < Cp; c += 4) {
+            float4 v;
+            v.x = c + 0 < C ? x[((size_t)n * C + c + 0) * HW + p] : 0.0f;
+            v.y = c + 1 < C ? x[((size_t)n * C + c + 1) * HW + p] : 0.0f;
+            v.z = c + 2 < C ? x[((size_t)n * C + c + 2) * HW + p] : 0.0f;
+            v.w = c + 3 < C ? x[((size_t)n * C + c + 3) * HW + p] : 0.0f;
+            act_st4(y, i * Cp + c, v);
+        }
+        return;
+    }
     for (int c = 0; c < Cp; ++c) act_st1(y, i * Cp + c, c < C ? x[((size_t)n * C + c) * HW + p] : 0.0f);
 }
 
@@ -57,15 +69,25 @@ __global__ void k_iuv_clean_global(int B, int HW, int Chead, int off_u, int off_
     const int best = argmax_first(I, 25);
     amax[i] = (uint8_t)best;
     const size_t o = (size_t)i * Cb;
+    // the cleaned row [U*onehot 25 | V*onehot 25 | onehot 25 | pad] (the products keep the reference's NaN/Inf
+    // propagation of `U * mask`), written as 4-channel vectors to every view
+    auto elem = [&](int cc) -> float {
+        if (cc < 25) return ((cc == best) ? 1.0f : 0.0f) * h[off_u + cc];
+        if (cc < 50) return ((cc - 25 == best) ? 1.0f : 0.0f) * h[off_v + cc - 25];
+        if (cc < 75) return (cc - 50 == best) ? 1.0f : 0.0f;
+        return 0.0f;
+    };
+    if ((Cb & 3) == 0) {
+        for (int c = 0; c < Cb; c += 4) act_st4(body, o + c, make_float4(elem(c), elem(c + 1), elem(c + 2), elem(c + 3)));
+    } else {
+        for (int c = 0; c < Cb; ++c) act_st1(body, o + c, elem(c));
+    }
     for (int c = 0; c < 25; ++c) {
         const float oh = (c == best) ? 1.0f : 0.0f;
-        const float u = oh * h[off_u + c], v = oh * h[off_v + c];
-        act_st1(body, o + c, u); act_st1(body, o + 25 + c, v); act_st1(body, o + 50 + c, oh);
-        if (un) un[((size_t)b * 25 + c) * HW + pix] = u;
-        if (vn) vn[((size_t)b * 25 + c) * HW + pix] = v;
+        if (un) un[((size_t)b * 25 + c) * HW + pix] = oh * h[off_u + c];
+        if (vn) vn[((size_t)b * 25 + c) * HW + pix] = oh * h[off_v + c];
         if (in_) in_[((size_t)b * 25 + c) * HW + pix] = oh;
     }
-    for (int c = 75; c < Cb; ++c) act_st1(body, o + c, 0.0f);
     if (an) {
 #pragma unroll
         for (int c = 0; c < 15; ++c) A[c] = h[off_a + c];

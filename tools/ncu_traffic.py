@@ -1,7 +1,7 @@
 """Sums dram bytes / duration of the conv launches of one bench step from an ncu CSV
 (metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum) -> profiles/conv_traffic.json"""
 import collections, csv, json, sys
-path, width, batch, convs_per_step = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+path, width, batch, convs_per_step = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])   # conv LAUNCHES per step (bench line: config.conv_path)
 lines = [l for l in open(path) if not l.startswith("==")]
 per = collections.defaultdict(lambda: collections.defaultdict(float))
 cnt = collections.Counter()

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "../../include/danet_b200.h"
@@ -53,9 +54,11 @@ __device__ __forceinline__ float warp_max(float v) {
 
 // cudaFuncSetAttribute is per device: true the first time the calling thread's current device is seen by this
 // call site (`mask` is the site's static bit set, one bit per device ordinal; -1 on error)
+inline std::mutex& first_use_mutex() { static std::mutex m; return m; }
 inline int first_use_on_current_device(unsigned long long* mask) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+    std::lock_guard<std::mutex> lk(first_use_mutex());       // host threads may make their first launch concurrently
     const bool first = !((*mask >> dev) & 1ull);
     *mask |= 1ull << dev;
     return first ? 1 : 0;

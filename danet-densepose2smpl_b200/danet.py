@@ -164,6 +164,11 @@ class DaNet(nn.Module):
     def plan_for(self, B, device, ops=None):
         """Compiled plan for batch size B (cached, LRU over MAX_PLANS batch sizes; packed weights are shared).
         `ops` replaces the kernel layer (plan.CudaOps) -- used by the host-logic tests, which drive a Plan directly."""
+        # plans snapshot the (folded, packed) weights: in-place parameter edits bump tensor versions and invalidate them
+        ver = sum(int(p._version) for p in self.parameters()) + sum(int(b._version) for b in self.buffers())
+        if ver != getattr(self, "_param_version", None):
+            self._invalidate()
+            self._param_version = ver
         key = (B, str(device), id(ops) if ops is not None else 0)
         if key in self._plans:
             self._plans[key] = self._plans.pop(key)            # most recently used last

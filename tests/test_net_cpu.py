@@ -143,3 +143,22 @@ def test_pretrained_flag_needs_files():
                          smpl_model=synthetic.make_smpl_model(0), dp_mesh=synthetic.make_dp_mesh(0))
     with pytest.raises(ValueError):
         danet_b200.DaNet(None, "/nonexistent/smpl_mean_params.npz", pretrained=False)
+
+
+def test_in_place_parameter_edit_invalidates_cached_plans():
+    """Plans snapshot folded / packed weights; an in-place edit of a parameter or buffer (tensor version bump) must
+    rebuild them (and the LRU keeps at most MAX_PLANS batch sizes)."""
+    net = build(32)
+    emul = TorchEmulOps()
+    img = make_image(1, 3)
+    a = infer_with_ops(net, img, emul)["para"].clone()
+    p1 = net.plan_for(1, img.device, ops=emul)
+    assert net.plan_for(1, img.device, ops=emul) is p1                 # cached
+    with torch.no_grad():
+        net.iuv2smpl.smpl_para_Outs.mean_cam_shape.add_(0.25)
+    b = infer_with_ops(net, img, emul)["para"]
+    assert net.plan_for(1, img.device, ops=emul) is not p1
+    assert (b[:, :13] - a[:, :13] - 0.25).abs().max() < 1e-5            # cam/shape = linear head + mean_cam_shape
+    for B in range(2, 2 + net.MAX_PLANS + 2):
+        net.plan_for(B, img.device, ops=emul)
+    assert len(net._plans) <= net.MAX_PLANS

@@ -109,6 +109,36 @@ __device__ __forceinline__ void act_st4(const ActV& a, size_t e, float4 v) {
         }
     }
 }
+// eight consecutive channels starting at element e (e % 8 == 0): 16-byte accesses on the fp16 planes
+struct float8 { float4 a, b; };
+__device__ __forceinline__ float8 act_ld8(const ActV& a, size_t e) {
+    float8 r;
+    if (a.f) { r.a = __ldg(reinterpret_cast<const float4*>(a.f + e)); r.b = __ldg(reinterpret_cast<const float4*>(a.f + e + 4)); return r; }
+    const uint4 h = __ldg(reinterpret_cast<const uint4*>(a.hi + e));
+    float2 p0 = h2_to_f2(h.x), p1 = h2_to_f2(h.y), p2 = h2_to_f2(h.z), p3 = h2_to_f2(h.w);
+    if (a.lo) {
+        const uint4 l = __ldg(reinterpret_cast<const uint4*>(a.lo + e));
+        const float2 q0 = h2_to_f2(l.x), q1 = h2_to_f2(l.y), q2 = h2_to_f2(l.z), q3 = h2_to_f2(l.w);
+        p0.x += q0.x; p0.y += q0.y; p1.x += q1.x; p1.y += q1.y; p2.x += q2.x; p2.y += q2.y; p3.x += q3.x; p3.y += q3.y;
+    }
+    r.a = make_float4(p0.x, p0.y, p1.x, p1.y); r.b = make_float4(p2.x, p2.y, p3.x, p3.y);
+    return r;
+}
+__device__ __forceinline__ void act_st8(const ActV& a, size_t e, const float8& v) {
+    if (a.f) { *reinterpret_cast<float4*>(a.f + e) = v.a; *reinterpret_cast<float4*>(a.f + e + 4) = v.b; }
+    if (a.hi) {
+        uint4 h;
+        h.x = pack_h2_rn(v.a.x, v.a.y); h.y = pack_h2_rn(v.a.z, v.a.w); h.z = pack_h2_rn(v.b.x, v.b.y); h.w = pack_h2_rn(v.b.z, v.b.w);
+        *reinterpret_cast<uint4*>(a.hi + e) = h;
+        if (a.lo) {
+            const float2 p0 = h2_to_f2(h.x), p1 = h2_to_f2(h.y), p2 = h2_to_f2(h.z), p3 = h2_to_f2(h.w);
+            uint4 l;
+            l.x = pack_h2_rn(v.a.x - p0.x, v.a.y - p0.y); l.y = pack_h2_rn(v.a.z - p1.x, v.a.w - p1.y);
+            l.z = pack_h2_rn(v.b.x - p2.x, v.b.y - p2.y); l.w = pack_h2_rn(v.b.z - p3.x, v.b.w - p3.y);
+            *reinterpret_cast<uint4*>(a.lo + e) = l;
+        }
+    }
+}
 __device__ __forceinline__ float act_ld1(const ActV& a, size_t e) {
     if (a.f) return __ldg(a.f + e);
     float v = __half2float(a.hi[e]);

@@ -109,9 +109,9 @@ static bool make_prob(const danet_conv_desc* d, int S_req, Prob* g) {
     const int ntmax = env_int(g->exact ? "DANET_TC_NTMAX_EXACT" : "DANET_TC_NTMAX_FAST", g->exact ? 128 : 256);
     g->ntn = (np + ntmax - 1) / ntmax;
     g->NT = ((np + g->ntn - 1) / g->ntn + 15) / 16 * 16;
-    // exact mode, k >= 3: a tap of [hi|lo] weight rows should not exceed 24 KB (one more N tile instead): the weight ring
+    // (experiment, off: measured 25.65 vs 24.79 ms/step) exact mode, k >= 3: cap a tap of [hi|lo] weight rows at 24 KB: the weight ring
     // keeps its depth and the layer can share a launch with the wide-halo branches (384-channel 7x7 maps: NT 128 -> 96)
-    if (g->exact && d->ksize >= 3 && 2 * g->NT * 128 > 24 * 1024 && env_int("DANET_TC_NTRULE", 1)) {
+    if (g->exact && d->ksize >= 3 && 2 * g->NT * 128 > 24 * 1024 && env_int("DANET_TC_NTRULE", 0)) {
         g->ntn += 1;
         g->NT = ((np + g->ntn - 1) / g->ntn + 15) / 16 * 16;
     }

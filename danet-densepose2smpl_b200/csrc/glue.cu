@@ -261,10 +261,12 @@ k_stn_params(int B, int S, int Chm, const float* __restrict__ hm, const uint8_t*
 // 24x affine_grid + grid_sample (iuv_estimator.py:193-204), C % 4 == 0
 // grid = one block per (crop b*24+part, output row py); threads run over (px, 4-channel group) of the row: the
 // per-element 64-bit div/mod chain of the first version cost more than the 16-byte store it fed
+// V = channels per work item: 8 when C % 8 == 0 (16-byte accesses on the fp16 planes), else 4; same arithmetic per channel
+template <int V>
 __global__ void __launch_bounds__(256)
 k_stn_sample(int B, int S, int C, ActV xd, const float* __restrict__ theta,
              int align_corners, ActV crops) {
-    const int C4 = C >> 2;
+    const int CV = C / V;
     const int bp = blockIdx.x / S, py = blockIdx.x - bp * S;
     const int b = bp / 24;
     const float* t = theta + (size_t)bp * 3;
@@ -281,10 +283,10 @@ k_stn_sample(int B, int S, int C, ActV xd, const float* __restrict__ theta,
     const bool y_ok = fy > -2.0f && fy < (float)S + 1.0f;
     const int y0 = y_ok ? (int)fy : 0;
     const size_t ibase = (size_t)b * S * S * C;
-    const size_t obase = ((size_t)bp * S + py) * S * C4;            // in 4-channel groups
-    const int items = S * C4;
+    const size_t obase = ((size_t)bp * S + py) * S * CV;            // in V-channel groups
+    const int items = S * CV;
     for (int i = threadIdx.x; i < items; i += blockDim.x) {
-        const int px = i / C4, c4 = i - px * C4;
+        const int px = i / CV, cv = i - px * CV;
         float xb;
         if (align_corners) xb = -1.0f + 2.0f * (float)px / (float)(S - 1);
         else xb = (float)(2 * px + 1) / (float)S - 1.0f;
@@ -294,7 +296,9 @@ k_stn_sample(int B, int S, int C, ActV xd, const float* __restrict__ theta,
         else ix = ((gx + 1.0f) * (float)S - 1.0f) * 0.5f;
         const float fx = floorf(ix);
         const float tx = ix - fx;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float acc[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] = 0.f;
         // guard against huge coordinates before the int conversion
         if (y_ok && fx > -2.0f && fx < (float)S + 1.0f) {
             const int x0 = (int)fx;
@@ -305,12 +309,25 @@ k_stn_sample(int B, int S, int C, ActV xd, const float* __restrict__ theta,
                     const int xx = x0 + dx, yy = y0 + dy;
                     if (xx < 0 || xx >= S || yy < 0 || yy >= S) continue;
                     const float w = (dx ? tx : 1.0f - tx) * (dy ? ty : 1.0f - ty);
-                    const float4 v = act_ld4(xd, ibase + (size_t)(yy * S + xx) * C + c4 * 4);
-                    acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
-                    acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+                    const size_t e = ibase + (size_t)(yy * S + xx) * C + cv * V;
+                    if (V == 8) {
+                        const float8 v = act_ld8(xd, e);
+                        acc[0] = fmaf(w, v.a.x, acc[0]); acc[1] = fmaf(w, v.a.y, acc[1]); acc[2] = fmaf(w, v.a.z, acc[2]); acc[3] = fmaf(w, v.a.w, acc[3]);
+                        acc[4 % V] = fmaf(w, v.b.x, acc[4 % V]); acc[5 % V] = fmaf(w, v.b.y, acc[5 % V]);
+                        acc[6 % V] = fmaf(w, v.b.z, acc[6 % V]); acc[7 % V] = fmaf(w, v.b.w, acc[7 % V]);
+                    } else {
+                        const float4 v = act_ld4(xd, e);
+                        acc[0] = fmaf(w, v.x, acc[0]); acc[1] = fmaf(w, v.y, acc[1]); acc[2] = fmaf(w, v.z, acc[2]); acc[3] = fmaf(w, v.w, acc[3]);
+                    }
                 }
         }
-        act_st4(crops, (obase + i) * 4, acc);
+        if (V == 8) {
+            float8 o;
+            o.a = make_float4(acc[0], acc[1], acc[2], acc[3]); o.b = make_float4(acc[4 % V], acc[5 % V], acc[6 % V], acc[7 % V]);
+            act_st8(crops, (obase + i) * 8, o);
+        } else {
+            act_st4(crops, (obase + i) * 4, make_float4(acc[0], acc[1], acc[2], acc[3]));
+        }
     }
 }
 
@@ -558,8 +575,13 @@ extern "C" int danet_stn_sample(int32_t B, int32_t S, int32_t C, const danet_act
     DANET_CHECK(theta, "danet_stn_sample: null pointer");
     if (check_act(xd, "danet_stn_sample(xd)", false, C) != 0 || check_act(crops, "danet_stn_sample(crops)", false, C) != 0) return -1;
     DANET_CHECK((int64_t)B * 24 * S < (1LL << 31), "danet_stn_sample: batch too large for one launch");
-    const int items = S * (C / 4);
-    k_stn_sample<<<B * 24 * S, items >= 256 ? 256 : (items + 31) / 32 * 32, 0, (cudaStream_t)s>>>(B, S, C, actv(xd), theta, align_corners, actv(crops));
+    if (C % 8 == 0) {
+        const int items = S * (C / 8);
+        k_stn_sample<8><<<B * 24 * S, items >= 256 ? 256 : (items + 31) / 32 * 32, 0, (cudaStream_t)s>>>(B, S, C, actv(xd), theta, align_corners, actv(crops));
+    } else {
+        const int items = S * (C / 4);
+        k_stn_sample<4><<<B * 24 * S, items >= 256 ? 256 : (items + 31) / 32 * 32, 0, (cudaStream_t)s>>>(B, S, C, actv(xd), theta, align_corners, actv(crops));
+    }
     DANET_LAUNCH_CHECK();
     return 0;
 }

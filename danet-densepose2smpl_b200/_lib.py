@@ -89,6 +89,15 @@ SIGNATURES = {
     "danet_stn_params": (c_int, [c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_f, c_int, c_p, c_p, c_p]),
     "danet_stn_sample": (c_int, [c_int, c_int, c_int, ctypes.POINTER(Act), c_p, c_int, ctypes.POINTER(Act), c_p]),
     "danet_gcn_pose_head": (c_int, [c_int, ctypes.POINTER(GcnParams), c_p, c_p, c_p, c_p]),
+    "danet_net_load": (c_int, [c_p, ctypes.c_uint64, ctypes.POINTER(c_p)]),
+    "danet_net_load_file": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_p)]),
+    "danet_net_destroy": (c_int, [c_p]),
+    "danet_net_info": (c_int, [c_p, c_p, c_p, c_p, c_p]),
+    "danet_net_output_name": (ctypes.c_char_p, [c_p, c_int]),
+    "danet_net_output": (c_int, [c_p, ctypes.c_char_p, ctypes.POINTER(c_p), ctypes.POINTER(ctypes.c_uint64), c_p, c_p]),
+    "danet_net_infer": (c_int, [c_p, c_p, c_int, c_p]),
+    "danet_net_infer_host": (c_int, [c_p, c_p, c_int]),
+    "danet_net_read_output": (c_int, [c_p, ctypes.c_char_p, c_p, ctypes.c_uint64]),
 }
 
 _lib = None

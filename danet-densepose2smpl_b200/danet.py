@@ -219,6 +219,14 @@ class DaNet(nn.Module):
         plan.run(image)
         return self.outputs_of(plan, B)
 
+    def export_program(self, batch_size, path=None):
+        """Network program of this model for one batch size (bytes; also written to `path`): what the C entry
+        danet_net_load / danet_net_infer replays without Python (include/danet_b200.h)."""
+        dev = self.img2iuv.learned_ratio.device
+        if dev.type != "cuda":
+            raise RuntimeError("danet_b200.DaNet: move the model to a CUDA device (there is no CPU path)")
+        return self.plan_for(batch_size, dev).export(path)
+
     def forward(self, in_dict):
         raise NotImplementedError("danet_b200.DaNet implements the inference path (infer_net); the training "
                                   "forward (danet.py:133-366) is out of scope (SURVEY section 8f)")

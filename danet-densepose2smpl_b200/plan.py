@@ -600,6 +600,171 @@ class Plan(object):
             self.static_in.copy_(image, non_blocking=True)
             self.graph_exec.replay()
 
+    # -- export ---------------------------------------------------------------------------------
+    OPCODES = {"input": 1, "conv_group": 2, "conv_simt": 3, "fuse": 4, "maxpool": 5, "avgpool": 6, "clean_global": 7,
+               "clean_parts": 8, "stn_params": 9, "stn_sample": 10, "linear": 11, "gcn_head": 12}
+    _DESC_KEYS = ("N", "H", "W", "Cin", "Cout", "ksize", "stride", "pad", "wsets", "relu", "flags")
+
+    def export(self, path=None):
+        """Serialise this plan as a network program for danet_net_load (csrc/net.cu, include/danet_b200.h): the launch
+        steps with their arguments, the activation buffer table and the folded / packed weights.  Returns the bytes
+        (and writes them to `path` when given).  The program is tied to this plan's batch size and precision."""
+        import struct
+        bufs, consts = {}, {}                          # storage ptr -> (id, nbytes) ; tensor ptr -> (id, tensor)
+
+        def bref(t):
+            if t is None:
+                return (0, 0, 0)
+            st = t.untyped_storage()
+            key = st.data_ptr()
+            if key not in bufs:
+                bufs[key] = (len(bufs), st.nbytes())
+            return (1, bufs[key][0], t.data_ptr() - key)
+
+        def cref(t):
+            if t is None:
+                return (0, 0, 0)
+            if not t.is_contiguous():
+                raise RuntimeError("export: constant tensors must be contiguous")
+            key = t.data_ptr()
+            if key not in consts:
+                consts[key] = (len(consts), t)
+            return (2, consts[key][0], 0)
+
+        def aref(a):
+            if a is None:
+                return [(0, 0, 0)] * 3
+            lo = a.h[1] if (a.h is not None and a.h.shape[0] > 1) else None
+            return [bref(a.f32), bref(a.h[0] if a.h is not None else None), bref(lo)]
+
+        def desc(d):
+            return [int(d.get(k, 0)) for k in self._DESC_KEYS]
+
+        steps = []                                      # (opcode, ints, floats, refs)
+        OP = self.OPCODES
+        for kind, op in self.steps:
+            if kind == "conv_group":
+                ints, refs = [len(op)], []
+                for cv in op:
+                    ints += desc(cv["d"])
+                    refs += aref(cv["x"]) + aref(cv["res"]) + aref(cv["y"]) + [cref(cv["w"]), cref(cv["b"])]
+                steps.append((OP[kind], ints, [], refs))
+            elif kind == "conv_simt":
+                res = op["res"].f32 if op["res"] is not None else None
+                steps.append((OP[kind], desc(op["d"]), [], [bref(op["x"].f32), cref(op["w"]), cref(op["b"]), bref(res), bref(op["y"].f32)]))
+            elif kind == "input":
+                y = self.T(op["y"])
+                t = y.f32 if y.f32 is not None else y.h[0]
+                Hin, Win = op["y"].H, op["y"].W
+                steps.append((OP[kind], [self.B, 3, Hin * Win, t.shape[-1]], [], [(3, 0, 0)] + aref(y)))
+            elif kind == "fuse":
+                N, H, W, C = self.shape(op["y"])
+                terms = op["terms"]
+                refs = []
+                for t, _f in terms:
+                    refs += aref(self.T(t))
+                steps.append((OP[kind], [N, H, W, C, len(terms), int(op["relu"])] + [int(f) for _, f in terms], [],
+                              refs + aref(self.T(op["y"]))))
+            elif kind == "maxpool":
+                steps.append((OP[kind], list(self.shape(op["x"])), [], aref(self.T(op["x"])) + aref(self.T(op["y"]))))
+            elif kind == "avgpool":
+                N, H, W, C = self.shape(op["x"])
+                steps.append((OP[kind], [N, H * W, C], [], aref(self.T(op["x"])) + [bref(self.T(op["y"]).f32)]))
+            elif kind == "clean_global":
+                x, y = op["x"], op["y"]
+                vis = self.vis if self.vis is not None else [None] * 4
+                steps.append((OP[kind], [self.B, x.H * x.W, x.Cp, 0, 25, 50, 75, y.Cp], [],
+                              [bref(self.T(x).f32)] + aref(self.T(y)) + [bref(self.T(op["amax"]))] + [bref(v) for v in vis]))
+            elif kind == "stn_params":
+                hm = self.T(op["hm"]).f32
+                steps.append((OP[kind], [hm.shape[0], hm.shape[1], hm.shape[3], int(self.align_corners)], [float(self.vis_thresh)],
+                              [bref(hm), bref(self.T(op["amax"])), cref(self.ratio), cref(self.offset),
+                               bref(self.T(op["centers"]).f32), bref(self.T(op["theta"]).f32)]))
+            elif kind == "stn_sample":
+                x = op["x"]
+                steps.append((OP[kind], [self.B, x.H, x.Cp, int(self.align_corners)], [],
+                              aref(self.T(x)) + [bref(self.T(op["theta"]).f32)] + aref(self.T(op["y"]))))
+            elif kind == "clean_parts":
+                x, y = op["x"], op["y"]
+                steps.append((OP[kind], [self.B * x.nmult, x.H * x.W, x.Cp, y.Cp], [],
+                              [bref(self.T(x).f32)] + aref(self.T(y)) + [bref(self.raw_parts)]))
+            elif kind == "body_fc":
+                N, H, W, C = self.shape(op["x"])
+                steps.append((OP["avgpool"], [N, H * W, C], [], aref(self.T(op["x"])) + [bref(self.pooled)]))
+                steps.append((OP["linear"], [N, self.fc_w.shape[1], self.fc_w.shape[0]], [],
+                              [bref(self.pooled), cref(self.fc_w), cref(self.fc_b), cref(self.fc_add), bref(self.T(op["y"]).f32)]))
+            elif kind == "gcn_head":
+                gp = self.gcn
+                ints = [self.B] + [int(w.shape[0]) for w in gp["W"]] + [int(w.shape[1]) for w in gp["W"]]
+                refs = [cref(gp["adj"])] + [cref(t) for t in gp["W"]] + [cref(t) for t in gp["b"]] + \
+                       [cref(t) for t in gp["bn_scale"]] + [cref(t) for t in gp["bn_shift"]] + \
+                       [cref(gp["head_w"]), cref(gp["head_b"]), cref(gp["mean_pose"]), bref(self.T(op["x"]).f32),
+                        bref(self.T(op["gpara"]).f32), bref(self.T(op["y"]).f32)]
+                steps.append((OP[kind], ints, [], refs))
+            else:
+                raise ValueError("export: unknown step %s" % kind)
+
+        outs = []                                       # (name, ref, elem_bytes, dims)
+        for k in self.KEEP:
+            if k not in self.g.outputs:
+                continue
+            a = self.T(self.g.outputs[k])
+            t = a if torch.is_tensor(a) else a.f32
+            outs.append((k, bref(t), t.element_size(), list(t.shape)))
+        if self.vis is not None:
+            for nm, t in zip(("vis_u", "vis_v", "vis_i", "vis_a"), self.vis):
+                outs.append((nm, bref(t), 4, list(t.shape)))
+            outs.append(("part_iuv_raw", bref(self.raw_parts), 4, list(self.raw_parts.shape)))
+
+        def pad16(b):
+            return b + b"\0" * (-len(b) % 16)
+
+        step_bytes = b""
+        for (code, ints, floats, refs) in steps:
+            step_bytes += struct.pack("<4I", code, len(ints), len(floats), len(refs))
+            step_bytes += struct.pack("<%di" % len(ints), *ints) + struct.pack("<%df" % len(floats), *floats)
+            for r in refs:
+                step_bytes += struct.pack("<IIQ", *r)
+        buf_list = sorted(bufs.values())
+        const_list = sorted(consts.values(), key=lambda c: c[0])
+        hdr_size = 8 + 12 * 4 + 4 * 8
+        tables_size = 8 * len(buf_list) + 16 * len(const_list) + 72 * len(outs)
+        steps_off = (hdr_size + tables_size + 15) // 16 * 16
+        payload_off = (steps_off + len(step_bytes) + 15) // 16 * 16
+        crecs, off = [], payload_off
+        for (_i, t) in const_list:
+            n = t.numel() * t.element_size()
+            crecs.append((off, n))
+            off += (n + 15) // 16 * 16
+        payload_bytes = off - payload_off
+        img = [op["y"] for kind, op in self.steps if kind == "input"][0]
+        Hin, Win = img.H, img.W
+        prec = 2 if not self.tc else (1 if self.precision == "exact" else 0)
+        blob = bytearray()
+        blob += b"DANETPRG" + struct.pack("<12I", 1, self.B, 3, Hin, Win, len(buf_list), len(const_list), len(outs), len(steps), prec, 0, 0)
+        blob += struct.pack("<4Q", steps_off, len(step_bytes), payload_off, payload_bytes)
+        for (_i, nbytes) in buf_list:
+            blob += struct.pack("<Q", nbytes)
+        for (o, n) in crecs:
+            blob += struct.pack("<QQ", o, n)
+        for (name, ref, eb, dims) in outs:
+            d = (list(dims) + [1, 1, 1, 1])[:4]
+            if len(dims) > 4:
+                raise RuntimeError("export: output %s has more than 4 dims" % name)
+            blob += name.encode()[:31].ljust(32, b"\0") + struct.pack("<IIQ", *ref) + struct.pack("<Ii4i", eb, len(dims), *d)
+        blob += b"\0" * (steps_off - len(blob))
+        blob += step_bytes
+        blob += b"\0" * (payload_off - len(blob))
+        with self._guard():
+            for (_i, t), (o, n) in zip(const_list, crecs):
+                assert len(blob) == o
+                blob += pad16(t.detach().reshape(-1).view(torch.uint8).cpu().numpy().tobytes())
+        blob = bytes(blob)
+        if path is not None:
+            with open(path, "wb") as f:
+                f.write(blob)
+        return blob
+
     def out(self, name):
         """fp32 tensor of a graph output."""
         a = self.T(self.g.outputs[name])

@@ -127,7 +127,7 @@ int danet_iuv_img2map(int32_t B, int32_t S, const float* img, float* maps_u, flo
                       float* maps_i, float* maps_ann, danet_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
- * Network half (models/danet/*, models/module/*).  NHWC activations as danet_act views (fp32 and/or
+ * Network half (models/danet/, models/module/).  NHWC activations as danet_act views (fp32 and/or
  * split-fp16 planes): every glue kernel below reads the fp32 view when present, else hi(+lo), and writes
  * every view that is present.
  * ------------------------------------------------------------------------------------------ */
@@ -256,6 +256,35 @@ typedef struct {
 int danet_gcn_pose_head(int32_t B, const danet_gcn_params* p, const float* rot_feats /*[B,24,128]*/,
                         const float* global_para /*[B,13]*/, float* para /*[B,229]*/,
                         danet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Whole-network entry (csrc/net.cu).  Replaces the network half of DaNet.infer_net
+ * (models/danet/danet.py:78-98: img2iuv -> iuvmap_clean -> iuv2smpl, up to `para`) for hosts without Python.
+ * A "network program" is what danet_b200.plan.Plan.export() writes for ONE batch size: the launch steps (each one of
+ * the entries above, with its arguments), the activation buffer table and the BN-folded, packed weights.  Loading
+ * allocates everything on the CURRENT device; infer replays the steps (optionally as one CUDA graph, captured on the
+ * first call).  Outputs stay in the program's buffers until the next infer:
+ *   "para" [B,229] f32 (cam 3 | shape 10 | 24 rotation matrices, danet.py:118), "centers" [B,24,2] (stn_kps_pred),
+ *   "theta", "global_para", "rot_feats", "heads", "hm", "body_iuv", "amax" (u8 [B,S,S]) and, when the plan kept the
+ *   visualisation maps, "vis_u" / "vis_v" / "vis_i" [B,25,S,S], "vis_a" [B,15,S,S], "part_iuv_raw" [B*24,21,S,S].
+ * ------------------------------------------------------------------------------------------ */
+typedef struct danet_net* danet_net_t;
+#define DANET_NET_GRAPH 1              /* flags: replay as a CUDA graph (a NULL stream is served by an internal blocking stream) */
+int danet_net_load(const void* program, uint64_t bytes, danet_net_t* out);         /* program: HOST memory */
+int danet_net_load_file(const char* path, danet_net_t* out);
+int danet_net_destroy(danet_net_t net);
+/* batch size, input [C,H,W], number of outputs, number of launch steps (any pointer may be NULL) */
+int danet_net_info(danet_net_t net, int32_t* batch, int32_t* chw, int32_t* n_outputs, int32_t* n_steps);
+const char* danet_net_output_name(danet_net_t net, int32_t index);                  /* NULL past the end */
+/* device pointer / byte size / dims[4] / element size of a named output */
+int danet_net_output(danet_net_t net, const char* name, void** dev_ptr, uint64_t* bytes, int32_t* dims,
+                     int32_t* elem_bytes);
+/* images: fp32 NCHW [B,C,H,W], device (or pinned host) memory; asynchronous on `stream` */
+int danet_net_infer(danet_net_t net, const float* images, int32_t flags, danet_stream_t stream);
+/* convenience for hosts that do not touch CUDA: pageable host images -> H2D -> steps -> synchronise (own stream) */
+int danet_net_infer_host(danet_net_t net, const float* images_host, int32_t flags);
+/* synchronous device -> host copy of a named output; `bytes` must equal the output's size */
+int danet_net_read_output(danet_net_t net, const char* name, void* host_dst, uint64_t bytes);
 
 #ifdef __cplusplus
 }

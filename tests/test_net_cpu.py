@@ -162,3 +162,37 @@ def test_in_place_parameter_edit_invalidates_cached_plans():
     for B in range(2, 2 + net.MAX_PLANS + 2):
         net.plan_for(B, img.device, ops=emul)
     assert len(net._plans) <= net.MAX_PLANS
+
+
+def test_network_program_export_is_well_formed():
+    """Plan.export (the input of danet_net_load, csrc/net.cu): every reference stays inside its buffer / constant, the
+    step list mirrors the plan's launch steps, the constants carry the packed weights byte for byte."""
+    from netprog_common import parse_program
+    net = build(32)
+    image = make_image(1, 3)
+    plan = net.plan_for(1, image.device, ops=TorchEmulOps())
+    plan.run(image)
+    blob = plan.export()
+    prog = parse_program(blob)
+    assert prog["version"] == 1 and prog["batch"] == 1 and prog["chw"] == (3, 224, 224) and prog["precision"] == 2
+    n_expected = sum(2 if kind == "body_fc" else 1 for kind, _ in plan.steps)
+    assert len(prog["steps"]) == n_expected
+    for s in prog["steps"]:
+        assert 1 <= s["op"] <= 12
+        for (kind, rid, roff) in s["refs"]:
+            assert kind in (0, 1, 2, 3)
+            if kind == 1:
+                assert rid < len(prog["bufs"]) and roff < prog["bufs"][rid]
+            if kind == 2:
+                assert rid < len(prog["consts"]) and roff == 0
+    names = [o["name"] for o in prog["outs"]]
+    assert "para" in names and "centers" in names and "vis_u" in names and "part_iuv_raw" in names
+    para = [o for o in prog["outs"] if o["name"] == "para"][0]
+    assert para["elem_bytes"] == 4 and int(np.prod(para["dims"])) >= 229
+    # a constant round-trips: the first conv step's weights
+    conv = [s for s in prog["steps"] if s["op"] == 3][0]
+    wref = conv["refs"][1]
+    coff, cbytes = prog["consts"][wref[1]]
+    first = [op for kind, op in plan.steps if kind == "conv_simt"][0]
+    assert cbytes == first["w"].numel() * 4
+    assert np.array_equal(np.frombuffer(blob, dtype=np.float32, count=first["w"].numel(), offset=coff), first["w"].reshape(-1).numpy())

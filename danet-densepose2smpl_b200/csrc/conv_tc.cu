@@ -372,6 +372,12 @@ __device__ __forceinline__ TileCoord decode_tile(const Prob& g, int t) {
 // ---------------------------------------------------------------------------------------------
 // PROF: bring-up instrumentation (per-role wait cycles); a separate instantiation so that the production kernel carries
 // none of its code
+// 256-bit global stores (sm_100: STG.E.ENL2.256): p must be 32-byte aligned
+__device__ __forceinline__ void st_global_v8(float* p, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+                 "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+
 template <bool PROF>
 __global__ void __launch_bounds__(kThreads, 1)
 k_conv_tc(const __grid_constant__ ArgsN a) {
@@ -779,7 +785,10 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
                     if (pon) { pwf += wseg; pseg += clock64() - tg0 - wseg; }
                 }
                 const long long tst0 = pon ? clock64() : 0;
-                // ReLU, split, store
+                // ReLU, split, store.  The fp32 view goes out in 256-bit stores (STG.E.ENL2.256, one full 32-byte sector per
+                // lane; channel offsets are multiples of 8 floats): measured 2x on the store phase of the SMPL blend-shape
+                // GEMM.  The fp16 planes stay with 16-byte stores: 256-bit stores were 10 % slower on the DRAM-write-bound
+                // 1x1 layers (tools/tc_layers.py, profiles/r02_epilogue_store_width.txt).
 #pragma unroll
                 for (int uu = 0; uu < 4; ++uu) {
                     if (!(okp[uu] && do_store)) continue;
@@ -794,10 +803,7 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
                             for (int j = 0; j < 8; ++j) ac[j] = fmaxf(ac[j], 0.f);
                         }
                         const uint32_t e = eoff[uu] + 8 * h;
-                        if (y_f) {
-                            *reinterpret_cast<float4*>(y_f + e) = make_float4(ac[0], ac[1], ac[2], ac[3]);
-                            *reinterpret_cast<float4*>(y_f + e + 4) = make_float4(ac[4], ac[5], ac[6], ac[7]);
-                        }
+                        if (y_f) st_global_v8(y_f + e, ac);
                         if (y_hi) {
                             uint4 hv;
                             hv.x = pack_h2_rn(ac[0], ac[1]); hv.y = pack_h2_rn(ac[2], ac[3]);

@@ -12,8 +12,8 @@
 //    of kGemmChunk bodies so that the fp32 v_posed chunk (85 MB) stays in the 126 MB L2 until the skinning
 //    kernel (the same k_smpl_verts, phase 1 replaced by a coalesced load) has consumed it.
 // Fused SIMT route, three launches per forward:
-//   k_smpl_pose    one thread per body: rotations, rest joints (linear in beta, precomputed
-//                  J_template + J_shapedirs*beta), chain -> A[B,24,3x4], pose_feature[B,208]
+//   k_smpl_pose    one warp per body, lane = joint: rotations, rest joints (linear in beta, precomputed
+//                  J_template + J_shapedirs*beta), chain level by level -> A[B,24,3x4], pose_feature[B,208]
 //   k_smpl_verts   grid (54 vertex tiles, B/NB body chunks), 128 threads:
 //                    phase 1 (coordinate-parallel, coalesced 4-byte lanes): v_posed for NB bodies,
 //                            posedirs/shapedirs rows reused from registers across the NB bodies
@@ -180,51 +180,64 @@ __global__ void k_mpjpe(int B, const float* __restrict__ j17, const float* __res
 // ---------------------------------------------------------------------------------------------
 // k_smpl_pose
 // ---------------------------------------------------------------------------------------------
-__global__ void k_smpl_pose(int B, int pose_kind, const float* __restrict__ betas,
-                            const float* __restrict__ pose, SmplView m, float* __restrict__ rot_out,
-                            float* __restrict__ G, float* __restrict__ A, float* __restrict__ pf,
-                            float* __restrict__ posed, __half* __restrict__ feat_hi, __half* __restrict__ feat_lo) {
-    // world transforms of the kinematic chain stay in shared memory (the parent's G is read back by
-    // the same thread; a global round trip cost ~1 us per joint)
-    __shared__ float s_G[32][kJ * 12 + 1];
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
+constexpr int kPoseWarps = 4;                       // bodies per CTA of k_smpl_pose (one warp each)
+__global__ void __launch_bounds__(kPoseWarps * 32)
+k_smpl_pose(int B, int pose_kind, const float* __restrict__ betas,
+            const float* __restrict__ pose, SmplView m, float* __restrict__ rot_out,
+            float* __restrict__ G, float* __restrict__ A, float* __restrict__ pf,
+            float* __restrict__ posed, __half* __restrict__ feat_hi, __half* __restrict__ feat_lo) {
+    // One warp per body, lane i < 24 = joint i.  The kinematic chain runs level by level: a lane fetches its
+    // parent's world transform with shuffles (tree depth 8 for SMPL), so the per-body serial work is 8 small
+    // matrix products instead of 24, every global access is a contiguous run of one body's data, and the
+    // expressions (and their order) are those of the one-thread-per-body form this replaces.
+    __shared__ float s_pf[kPoseWarps][kGF];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * kPoseWarps + warp;
+    if (b >= B) return;                                  // whole warps leave together
+    const int i = lane < kJ ? lane : 0;                  // lanes 24..31 shadow joint 0 (they write nothing)
+    const bool act = lane < kJ;
     float beta[kMaxBetas];
     for (int l = 0; l < m.nbetas; ++l) beta[l] = betas[(size_t)b * m.nbetas + l];
-    float J[kJ * 3];
-    for (int e = 0; e < kJ * 3; ++e) {
+    float Ji[3];
+    for (int r = 0; r < 3; ++r) {
+        const int e = i * 3 + r;
         float v = m.Jt[e];
         for (int l = 0; l < m.nbetas; ++l) v = fmaf(beta[l], m.Jsd[e * m.nbetas + l], v);
-        J[e] = v;
+        Ji[r] = v;
     }
-    float* Gb = s_G[threadIdx.x];
-    float* Ab = A + (size_t)b * kJ * 12;
-    float* pfb = pf + (size_t)b * kPF;
-    for (int i = 0; i < kJ; ++i) {
-        float R[9];
-        if (pose_kind == DANET_POSE_ROTMAT) {
-            for (int e = 0; e < 9; ++e) R[e] = pose[((size_t)b * kJ + i) * 9 + e];
-        } else if (pose_kind == DANET_POSE_AXIS_ANGLE) {
-            const float v[3] = {pose[((size_t)b * kJ + i) * 3], pose[((size_t)b * kJ + i) * 3 + 1],
-                                pose[((size_t)b * kJ + i) * 3 + 2]};
-            rodrigues_smplx(v, R);
-        } else {
-            float v[6];
-            for (int e = 0; e < 6; ++e) v[e] = pose[((size_t)b * kJ + i) * 6 + e];
-            rot6d(v, R);
-        }
-        if (rot_out) for (int e = 0; e < 9; ++e) rot_out[((size_t)b * kJ + i) * 9 + e] = R[e];
-        if (i > 0) for (int e = 0; e < 9; ++e) pfb[(i - 1) * 9 + e] = R[e] - ((e % 4 == 0) ? 1.0f : 0.0f);
-        float g[12];
-        if (i == 0) {
-            for (int r = 0; r < 3; ++r) {
-                g[r * 4 + 0] = R[r * 3 + 0]; g[r * 4 + 1] = R[r * 3 + 1]; g[r * 4 + 2] = R[r * 3 + 2];
-                g[r * 4 + 3] = J[r];
-            }
-        } else {
-            const int p = m.parents[i];
-            const float* gp = Gb + p * 12;
-            const float rel[3] = {J[i * 3] - J[p * 3], J[i * 3 + 1] - J[p * 3 + 1], J[i * 3 + 2] - J[p * 3 + 2]};
+    float R[9];
+    if (pose_kind == DANET_POSE_ROTMAT) {
+        for (int e = 0; e < 9; ++e) R[e] = pose[((size_t)b * kJ + i) * 9 + e];
+    } else if (pose_kind == DANET_POSE_AXIS_ANGLE) {
+        const float v[3] = {pose[((size_t)b * kJ + i) * 3], pose[((size_t)b * kJ + i) * 3 + 1],
+                            pose[((size_t)b * kJ + i) * 3 + 2]};
+        rodrigues_smplx(v, R);
+    } else {
+        float v[6];
+        for (int e = 0; e < 6; ++e) v[e] = pose[((size_t)b * kJ + i) * 6 + e];
+        rot6d(v, R);
+    }
+    if (rot_out && act) for (int e = 0; e < 9; ++e) rot_out[((size_t)b * kJ + i) * 9 + e] = R[e];
+    if (act && i > 0) for (int e = 0; e < 9; ++e) s_pf[warp][(i - 1) * 9 + e] = R[e] - ((e % 4 == 0) ? 1.0f : 0.0f);
+    // depth of this joint in the tree, and the deepest level
+    const int p = i > 0 ? m.parents[i] : 0;
+    int depth = 0;
+    for (int q = i; q > 0; q = m.parents[q]) ++depth;
+    int maxd = act ? depth : 0;
+    for (int o = 16; o > 0; o >>= 1) maxd = max(maxd, __shfl_xor_sync(0xffffffffu, maxd, o));
+    float rel[3];
+    for (int r = 0; r < 3; ++r) rel[r] = Ji[r] - __shfl_sync(0xffffffffu, Ji[r], p);
+    float g[12];
+    for (int r = 0; r < 3; ++r) {                        // the root's transform; every other lane overwrites it at its level
+        g[r * 4 + 0] = R[r * 3 + 0]; g[r * 4 + 1] = R[r * 3 + 1]; g[r * 4 + 2] = R[r * 3 + 2];
+        g[r * 4 + 3] = Ji[r];
+    }
+    for (int d = 1; d <= maxd; ++d) {
+        float gp[12];
+#pragma unroll
+        for (int e = 0; e < 12; ++e) gp[e] = __shfl_sync(0xffffffffu, g[e], p);
+        if (depth == d) {
+#pragma unroll
             for (int r = 0; r < 3; ++r) {
                 const float a0 = gp[r * 4], a1 = gp[r * 4 + 1], a2 = gp[r * 4 + 2], a3 = gp[r * 4 + 3];
                 g[r * 4 + 0] = a0 * R[0] + a1 * R[3] + a2 * R[6];
@@ -233,29 +246,33 @@ __global__ void k_smpl_pose(int B, int pose_kind, const float* __restrict__ beta
                 g[r * 4 + 3] = a0 * rel[0] + a1 * rel[1] + a2 * rel[2] + a3;
             }
         }
-        for (int e = 0; e < 12; ++e) Gb[i * 12 + e] = g[e];
-        if (G) for (int e = 0; e < 12; ++e) G[((size_t)b * kJ + i) * 12 + e] = g[e];      // world transforms (backward pass)
+    }
+    if (act) {
+        if (G) {                                         // world transforms (backward pass)
+            float4* Gv = reinterpret_cast<float4*>(G + ((size_t)b * kJ + i) * 12);
+            Gv[0] = make_float4(g[0], g[1], g[2], g[3]); Gv[1] = make_float4(g[4], g[5], g[6], g[7]); Gv[2] = make_float4(g[8], g[9], g[10], g[11]);
+        }
+        float a[12];
         for (int r = 0; r < 3; ++r) {
             posed[((size_t)b * kJ + i) * 3 + r] = g[r * 4 + 3];
-            Ab[i * 12 + r * 4 + 0] = g[r * 4 + 0];
-            Ab[i * 12 + r * 4 + 1] = g[r * 4 + 1];
-            Ab[i * 12 + r * 4 + 2] = g[r * 4 + 2];
-            Ab[i * 12 + r * 4 + 3] = g[r * 4 + 3] -
-                (g[r * 4 + 0] * J[i * 3] + g[r * 4 + 1] * J[i * 3 + 1] + g[r * 4 + 2] * J[i * 3 + 2]);
+            a[r * 4 + 0] = g[r * 4 + 0]; a[r * 4 + 1] = g[r * 4 + 1]; a[r * 4 + 2] = g[r * 4 + 2];
+            a[r * 4 + 3] = g[r * 4 + 3] - (g[r * 4 + 0] * Ji[0] + g[r * 4 + 1] * Ji[1] + g[r * 4 + 2] * Ji[2]);
         }
+        float4* Av = reinterpret_cast<float4*>(A + ((size_t)b * kJ + i) * 12);
+        Av[0] = make_float4(a[0], a[1], a[2], a[3]); Av[1] = make_float4(a[4], a[5], a[6], a[7]); Av[2] = make_float4(a[8], a[9], a[10], a[11]);
     }
-    pfb[207] = 0.0f;
-    if (feat_hi) {
-        // GEMM route: [pose feature (207) | 0 | betas | 0 ...] as split-fp16 planes (hi = rn(v), lo = rn(v - hi))
-        __half* fh = feat_hi + (size_t)b * kGF;
-        __half* fl = feat_lo + (size_t)b * kGF;
-        for (int k = 0; k < kGF; ++k) {
-            float v = 0.0f;
-            if (k < 207) v = pfb[k];
-            else if (k >= 208 && k - 208 < m.nbetas) v = beta[k - 208];
+    __syncwarp();
+    // pose feature [207 | 0] (fp32) and, on the GEMM route, [pose feature | 0 | betas | 0 ...] as split-fp16 planes
+    // (hi = rn(v), lo = rn(v - hi)): lanes sweep the row, coalesced
+    for (int k = lane; k < kGF; k += 32) {
+        float v = 0.0f;
+        if (k < 207) v = s_pf[warp][k];
+        if (k < kPF) pf[(size_t)b * kPF + k] = v;
+        if (feat_hi) {
+            if (k >= 208 && k - 208 < m.nbetas) v = beta[k - 208];
             const __half h = __float2half_rn(v);
-            fh[k] = h;
-            fl[k] = __float2half_rn(v - __half2float(h));
+            feat_hi[(size_t)b * kGF + k] = h;
+            feat_lo[(size_t)b * kGF + k] = __float2half_rn(v - __half2float(h));
         }
     }
 }
@@ -263,6 +280,144 @@ __global__ void k_smpl_pose(int B, int pose_kind, const float* __restrict__ beta
 // ---------------------------------------------------------------------------------------------
 // k_smpl_verts
 // ---------------------------------------------------------------------------------------------
+// k_smpl_skin: the skinning + store + regressor-partial phases of k_smpl_verts for the tensor-core route, where
+// v_posed is already in memory (L2-resident GEMM output).  One CTA walks TL consecutive vertex tiles of its NB bodies:
+// the bone transforms are loaded once (they were 38 % of the old kernel's read traffic: 54 tiles x 1152 B per body) and
+// tile k+1's v_posed rows stream into the second shared-memory buffer (cp.async, 16-byte chunks) while tile k is skinned.
+__device__ __forceinline__ void cp_async16_zfill(float* smem_dst, const float* gsrc, int src_bytes) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+template <int NB, int TL>
+__global__ void __launch_bounds__(kTileV)
+k_smpl_skin(int B, const float* __restrict__ A, SmplView m, float* __restrict__ verts, float* __restrict__ partials,
+            const float* __restrict__ vposed, int vp_stride) {
+    extern __shared__ __align__(16) float smem_lbs[];
+    float (*s_A)[kJ * 12] = reinterpret_cast<float (*)[kJ * 12]>(smem_lbs);
+    float* s_vbuf = smem_lbs + NB * kJ * 12;                       // [2][NB][kTileC]
+    const int b0 = blockIdx.y * NB, tid = threadIdx.x, t0 = blockIdx.x * TL;
+    constexpr int kChunks = kTileC / 4;                              // 16-byte chunks per body row of a tile
+
+    auto issue = [&](int tile, int buf) {
+        for (int i = tid; i < NB * kChunks; i += kTileV) {
+            const int b = i / kChunks, c = i - b * kChunks, bb = min(b0 + b, B - 1);
+            const int n = tile * kTileC + 4 * c;
+            const bool ok = n + 4 <= vp_stride;                      // the last tile runs past the row: zero fill
+            cp_async16_zfill(s_vbuf + ((size_t)(buf * NB + b) * kTileC + 4 * c), vposed + (size_t)bb * vp_stride + (ok ? n : 0), ok ? 16 : 0);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue(t0, 0);
+    for (int i = tid; i < NB * kJ * 12; i += kTileV) {
+        const int b = i / (kJ * 12), k = i % (kJ * 12), bb = min(b0 + b, B - 1);
+        s_A[b][k] = A[(size_t)bb * kJ * 12 + k];
+    }
+    const int ncoord = m.nv * 3;
+    const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll 1
+    for (int kt = 0; kt < TL; ++kt) {
+        const int tile = t0 + kt;
+        if (kt + 1 < TL) {
+            issue(tile + 1, (kt + 1) & 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        float (*s_v)[kTileC] = reinterpret_cast<float (*)[kTileC]>(s_vbuf + (size_t)(kt & 1) * NB * kTileC);
+        // ---- skinning, thread = vertex (<= 4 bones per vertex) ----
+        {
+            const int v = tile * kTileV + tid;
+            const uint32_t idx = __ldg(m.skin_idx + v);
+            const float4 w = __ldg(m.skin_w + v);
+            const int j0 = idx & 255, j1 = (idx >> 8) & 255, j2 = (idx >> 16) & 255, j3 = idx >> 24;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                const float x = s_v[b][3 * tid], y = s_v[b][3 * tid + 1], z = s_v[b][3 * tid + 2];
+                const float4* A0 = reinterpret_cast<const float4*>(&s_A[b][j0 * 12]);
+                const float4* A1 = reinterpret_cast<const float4*>(&s_A[b][j1 * 12]);
+                const float4* A2 = reinterpret_cast<const float4*>(&s_A[b][j2 * 12]);
+                const float4* A3 = reinterpret_cast<const float4*>(&s_A[b][j3 * 12]);
+                float o[3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {                    // one 16-byte row of each bone's 3x4 transform
+                    const float4 a0 = A0[r], a1 = A1[r], a2 = A2[r], a3 = A3[r];
+                    const float t0 = w.x * a0.x + w.y * a1.x + w.z * a2.x + w.w * a3.x;
+                    const float t1 = w.x * a0.y + w.y * a1.y + w.z * a2.y + w.w * a3.y;
+                    const float t2 = w.x * a0.z + w.y * a1.z + w.z * a2.z + w.w * a3.z;
+                    const float t3 = w.x * a0.w + w.y * a1.w + w.z * a2.w + w.w * a3.w;
+                    o[r] = t0 * x + t1 * y + t2 * z + t3;
+                }
+                s_v[b][3 * tid] = o[0]; s_v[b][3 * tid + 1] = o[1]; s_v[b][3 * tid + 2] = o[2];
+            }
+        }
+        __syncthreads();
+        // ---- coalesced store + joint-regressor partial sums ----
+        if (verts) {
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                if (b0 + b < B) {
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const int gn = tile * kTileC + tid + j * kTileV;
+                        if (gn < ncoord) verts[(size_t)(b0 + b) * ncoord + gn] = s_v[b][tid + j * kTileV];
+                    }
+                }
+            }
+        }
+        const int off = m.tile_pair_off[tile], npair = m.tile_pair_off[tile + 1] - off;
+        // one warp per (tile, regressor row) pair, all NB bodies at once: 3 NB partial sums per lane, reduced across the
+        // warp by halving the value set at every shuffle step (27 shuffles instead of 15 per body)
+        static_assert(NB == 8, "the transposed reduction below is written for 8 bodies (24 values over 32 lanes)");
+        for (int pr = warp; pr < npair; pr += kTileV / 32) {
+            const int row = m.tile_pair_row[off + pr];
+            const float* rr = m.reg_rows + (size_t)row * m.nvpad + (size_t)tile * kTileV;
+            float r4[kTileV / 32];
+#pragma unroll
+            for (int i = 0; i < kTileV / 32; ++i) r4[i] = __ldg(rr + lane + i * 32);
+            float acc[NB * 3];
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                for (int i = 0; i < kTileV / 32; ++i) {
+                    const int vv = lane + i * 32;
+                    s0 = fmaf(r4[i], s_v[b][3 * vv], s0);
+                    s1 = fmaf(r4[i], s_v[b][3 * vv + 1], s1);
+                    s2 = fmaf(r4[i], s_v[b][3 * vv + 2], s2);
+                }
+                acc[3 * b] = s0; acc[3 * b + 1] = s1; acc[3 * b + 2] = s2;
+            }
+            const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+            float w12[12], w6[6], w3[3];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+                const float keep = h16 ? acc[k + 12] : acc[k], send = h16 ? acc[k] : acc[k + 12];
+                w12[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const float keep = h8 ? w12[k + 6] : w12[k], send = h8 ? w12[k] : w12[k + 6];
+                w6[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float keep = h4 ? w6[k + 3] : w6[k], send = h4 ? w6[k] : w6[k + 3];
+                float v = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                w3[k] = v;
+            }
+            const int body = lane >> 2;                            // lanes 4g hold body g = bit4*4 + bit3*2 + bit2
+            if ((lane & 3) == 0 && b0 + body < B) {
+                float* dst = partials + ((size_t)(b0 + body) * m.npairs + off + pr) * 3;
+                dst[0] = w3[0]; dst[1] = w3[1]; dst[2] = w3[2];
+            }
+        }
+        __syncthreads();                                             // the buffer is refilled two tiles later
+    }
+}
+
 template <int NB>
 __global__ void __launch_bounds__(kTileV)
 k_smpl_verts(int B, const float* __restrict__ betas, const float* __restrict__ pf,
@@ -818,7 +973,7 @@ extern "C" int danet_smpl_forward(danet_smpl_t h, int32_t B, const float* betas,
         feat_lo = (__half*)(ws + ws_off(cur, Bp * kGF * 2));
         vposed = (float*)(ws + ws_off(cur, (int64_t)(B < kGemmChunk ? Bp : kGemmChunk) * h->gemm_cout * 4));
     }
-    k_smpl_pose<<<cdiv(B, 32), 32, 0, stream>>>(B, pose_kind, betas, pose, m, rotmats, nullptr, A, pf, posed, feat_hi, feat_lo);
+    k_smpl_pose<<<cdiv(B, kPoseWarps), kPoseWarps * 32, 0, stream>>>(B, pose_kind, betas, pose, m, rotmats, nullptr, A, pf, posed, feat_hi, feat_lo);
     (void)G;
     DANET_LAUNCH_CHECK();
     int nb = bodies_per_cta;
@@ -847,7 +1002,16 @@ extern "C" int danet_smpl_forward(danet_smpl_t h, int32_t B, const float* betas,
             pr.x.hi = feat_hi + (size_t)off * kGF; pr.x.lo = feat_lo + (size_t)off * kGF;
             pr.y.f32 = vposed; pr.w_packed = h->gemm_w; pr.bias = h->gemm_bias;
             if (conv_tc_group_launch(1, &pr, stream) != 0) return -1;
-            DANET_LBS_LAUNCH(8, Bc, off, vposed);
+            constexpr int kSkinTL = 3;                                  // vertex tiles per CTA of the skinning pass
+            if (m.skin_packed && m.ntiles % kSkinTL == 0) {
+                dim3 grid(m.ntiles / kSkinTL, cdiv(Bc, 8));
+                const size_t sm = (size_t)8 * (kJ * 12 + 2 * kTileC) * sizeof(float);
+                k_smpl_skin<8, kSkinTL><<<grid, kTileV, sm, stream>>>(Bc, A + (size_t)off * kJ * 12, m,
+                    verts ? verts + (size_t)off * m.nv * 3 : nullptr, partials + (size_t)off * (m.npairs > 0 ? m.npairs : 1) * 3,
+                    vposed, h->gemm_cout);
+            } else {
+                DANET_LBS_LAUNCH(8, Bc, off, vposed);
+            }
             DANET_LAUNCH_CHECK();
         }
     } else {
@@ -902,7 +1066,7 @@ extern "C" int danet_smpl_backward(danet_smpl_t h, int32_t B, const float* betas
     float* dA = (float*)(ws + ws_off(cur, (int64_t)B * kJ * 12 * 4));
     float* dpf = (float*)(ws + ws_off(cur, (int64_t)B * kPF * 4));
     DANET_CUDA(cudaMemsetAsync(dA, 0, (size_t)B * kJ * 12 * 4, stream));
-    k_smpl_pose<<<cdiv(B, 32), 32, 0, stream>>>(B, DANET_POSE_ROTMAT, betas, rotmats, m, nullptr, G, A, pf, posed, nullptr, nullptr);
+    k_smpl_pose<<<cdiv(B, kPoseWarps), kPoseWarps * 32, 0, stream>>>(B, DANET_POSE_ROTMAT, betas, rotmats, m, nullptr, G, A, pf, posed, nullptr, nullptr);
     DANET_LAUNCH_CHECK();
     k_lbs_bwd_verts<<<dim3(m.ntiles, B), kTileV, 0, stream>>>(B, betas, pf, A, m, grad_verts, dvp, dA);
     DANET_LAUNCH_CHECK();

@@ -317,6 +317,21 @@ k_smpl_skin(int B, const float* __restrict__ A, SmplView m, float* __restrict__ 
 #pragma unroll 1
     for (int kt = 0; kt < TL; ++kt) {
         const int tile = t0 + kt;
+        // everything this tile needs from global memory that does not depend on v_posed is requested before the wait:
+        // the vertex's bones and weights, the tile's regressor rows (first pair of this warp)
+        const int v = tile * kTileV + tid;
+        const uint32_t idx = __ldg(m.skin_idx + v);
+        const float4 w = __ldg(m.skin_w + v);
+        const int off = m.tile_pair_off[tile], npair = m.tile_pair_off[tile + 1] - off;
+        float r4n[kTileV / 32];
+        auto load_pair = [&](int pr, float* r4) {
+            if (pr < npair) {
+                const float* rr = m.reg_rows + (size_t)m.tile_pair_row[off + pr] * m.nvpad + (size_t)tile * kTileV;
+#pragma unroll
+                for (int i = 0; i < kTileV / 32; ++i) r4[i] = __ldg(rr + lane + i * 32);
+            }
+        };
+        load_pair(warp, r4n);
         if (kt + 1 < TL) {
             issue(tile + 1, (kt + 1) & 1);
             asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -327,9 +342,6 @@ k_smpl_skin(int B, const float* __restrict__ A, SmplView m, float* __restrict__ 
         float (*s_v)[kTileC] = reinterpret_cast<float (*)[kTileC]>(s_vbuf + (size_t)(kt & 1) * NB * kTileC);
         // ---- skinning, thread = vertex (<= 4 bones per vertex) ----
         {
-            const int v = tile * kTileV + tid;
-            const uint32_t idx = __ldg(m.skin_idx + v);
-            const float4 w = __ldg(m.skin_w + v);
             const int j0 = idx & 255, j1 = (idx >> 8) & 255, j2 = (idx >> 16) & 255, j3 = idx >> 24;
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
@@ -365,16 +377,14 @@ k_smpl_skin(int B, const float* __restrict__ A, SmplView m, float* __restrict__ 
                 }
             }
         }
-        const int off = m.tile_pair_off[tile], npair = m.tile_pair_off[tile + 1] - off;
         // one warp per (tile, regressor row) pair, all NB bodies at once: 3 NB partial sums per lane, reduced across the
         // warp by halving the value set at every shuffle step (27 shuffles instead of 15 per body)
         static_assert(NB == 8, "the transposed reduction below is written for 8 bodies (24 values over 32 lanes)");
         for (int pr = warp; pr < npair; pr += kTileV / 32) {
-            const int row = m.tile_pair_row[off + pr];
-            const float* rr = m.reg_rows + (size_t)row * m.nvpad + (size_t)tile * kTileV;
             float r4[kTileV / 32];
 #pragma unroll
-            for (int i = 0; i < kTileV / 32; ++i) r4[i] = __ldg(rr + lane + i * 32);
+            for (int i = 0; i < kTileV / 32; ++i) r4[i] = r4n[i];
+            load_pair(pr + kTileV / 32, r4n);                        // next pair's row while this one is reduced
             float acc[NB * 3];
 #pragma unroll
             for (int b = 0; b < NB; ++b) {

@@ -394,6 +394,14 @@ def parity_block(net, dev, width, B):
         R = p[:, 13:].reshape(-1, 24, 3, 3)
         return smpl(betas=p[:, 3:13].contiguous(), body_pose=R[:, 1:], global_orient=R[:, :1], pose2rot=False).vertices
     dv = (verts(para) - verts(ref)).norm(dim=-1)
+    # eval.py:196-212 on both: MPJPE against synthetic ground-truth joints, from our para and from the reference's
+    from danet_b200.smpl import mpjpe_h36m
+    gt = (torch.randn(B, 14, 3, generator=torch.Generator().manual_seed(5)) * 0.2).to(dev)
+    mp = []
+    for p in (para, ref):
+        verts(p)
+        j17 = smpl.joints_h36m()
+        mp.append(mpjpe_h36m(j17, gt).cpu().numpy() * 1e3 if j17 is not None else None)
     u, v, i, a = out["visualization"]["iuv_pred"]
     idx = i.argmax(1).cpu().numpy()
     ann = a.argmax(1).cpu().numpy()
@@ -416,7 +424,13 @@ def parity_block(net, dev, width, B):
             "para_max_abs_err_flipped_images": float(err[dirty].max()) if dirty.any() else 0.0,
             "verts_max_err_mm_flipped_images": float(dvn[dirty].max()) if dirty.any() else 0.0,
             "stn_kps_max_abs_err": float((out["stn_kps_pred"].cpu() - torch.from_numpy(g["stn_kps"])).abs().max()),
-            "verts_mean_err_mm": float(dv.mean()) * 1e3}
+            "verts_mean_err_mm": float(dv.mean()) * 1e3,
+            "mpjpe_mm": None if mp[0] is None else {
+                "note": "eval.py:196-212 on synthetic ground truth, from this path's para vs from the reference's para",
+                "mean_this": float(mp[0].mean()), "mean_reference": float(mp[1].mean()),
+                "mean_abs_diff": float(abs(mp[0].mean() - mp[1].mean())),
+                "per_image_max_abs_diff": float(np.abs(mp[0] - mp[1]).max()),
+                "per_image_median_abs_diff": float(np.median(np.abs(mp[0] - mp[1])))}}
 
 
 def time_net(net, smpl, rend, x, iters):

@@ -460,6 +460,8 @@ k_gcn_pose_head(int B, GcnArgs g, const float* __restrict__ rot_feats, const flo
             const float* W = g.W[l];
             // 4 input features per step: 4 independent weight loads in flight and one 16-byte
             // broadcast smem read per node instead of four scalar ones (the loop was LDS-bound)
+            // (unrolled x4: 16 weight loads in flight -- one L2 round trip per 16 input features instead of per 4)
+#pragma unroll 4
             for (int f = 0; f < F; f += 4) {
                 const float w0 = __ldg(W + (size_t)f * Fo + tid), w1 = __ldg(W + (size_t)(f + 1) * Fo + tid);
                 const float w2 = __ldg(W + (size_t)(f + 2) * Fo + tid), w3 = __ldg(W + (size_t)(f + 3) * Fo + tid);
@@ -486,6 +488,7 @@ k_gcn_pose_head(int B, GcnArgs g, const float* __restrict__ rot_feats, const flo
         const int j = tid / 6, k = tid % 6;
         const float* w = g.head_w + ((size_t)j * 6 + k) * 128;
         float s = 0.f;
+#pragma unroll 16
         for (int f = 0; f < 128; ++f) s = fmaf(s_x[j * kGcnMaxF + f], __ldg(w + f), s);
         s_p6[tid] = s + g.head_b[tid] + g.mean_pose[tid];
     }

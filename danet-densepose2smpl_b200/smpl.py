@@ -212,11 +212,45 @@ class SMPL(nn.Module):
         return ws
 
     # -- forward ----------------------------------------------------------------------------
-    @torch.no_grad()
     def forward(self, betas=None, body_pose=None, global_orient=None, transl=None, return_verts=True,
                 return_full_pose=False, pose2rot=True, pose6d=None, bodies_per_cta=0, **kwargs):
         """betas [B,10]; body_pose [B,23,3,3] | [B,69]; global_orient [B,1,3,3] | [B,3].
-        `pose6d` [B,24,6] (extension): feed the network's 6-d output directly (rot6d front-end)."""
+        `pose6d` [B,24,6] (extension): feed the network's 6-d output directly (rot6d front-end).
+        With autograd enabled and an input that requires grad, the rotation-matrix mode (pose2rot=False: what the
+        training step feeds, smpl_regressor.py:170) is differentiable: vertices / joints / smpl_joints back-propagate into
+        betas and the rotation matrices through danet_smpl_backward (csrc/lbs.cu)."""
+        wants_grad = torch.is_grad_enabled() and any(
+            t is not None and torch.is_tensor(t) and t.requires_grad for t in (betas, body_pose, global_orient, pose6d))
+        if wants_grad:
+            if pose2rot or pose6d is not None:
+                raise NotImplementedError("danet_b200.SMPL: gradients are implemented for rotation-matrix inputs "
+                                          "(pose2rot=False), the mode the reference trains with")
+            return self._forward_autograd(betas, body_pose, global_orient, transl, return_verts, return_full_pose)
+        with torch.no_grad():
+            return self._forward_impl(betas, body_pose, global_orient, transl, return_verts, return_full_pose, pose2rot,
+                                      pose6d, bodies_per_cta)
+
+    def _forward_autograd(self, betas, body_pose, global_orient, transl, return_verts, return_full_pose):
+        dev = self.v_template.device
+        if dev.type != "cuda":
+            raise RuntimeError("danet_b200.SMPL: move the module to a CUDA device first (no CPU path)")
+        B = next(t for t in (betas, body_pose, global_orient) if t is not None).shape[0]
+        f = lambda t: t.to(device=dev, dtype=torch.float32)
+        eye = torch.eye(3, device=dev)
+        betas = torch.zeros(B, self.shapedirs.shape[-1], device=dev) if betas is None else f(betas)
+        go = eye.expand(B, 1, 3, 3) if global_orient is None else f(global_orient).reshape(B, 1, 3, 3)
+        bp = eye.expand(B, 23, 3, 3) if body_pose is None else f(body_pose).reshape(B, 23, 3, 3)
+        verts, joints, smpl_joints = _SmplLbs.apply(self, betas, torch.cat([go, bp], dim=1))
+        if transl is not None:
+            t = transl.to(dev, torch.float32).unsqueeze(1)
+            joints, verts, smpl_joints = joints + t, verts + t, smpl_joints + t
+        joints_J19 = joints[:, -24:, :][:, constants.J24_TO_J19, :]
+        return self.ModelOutput(vertices=verts if return_verts else None, global_orient=go, body_pose=bp, joints=joints,
+                                joints_J19=joints_J19, smpl_joints=smpl_joints, betas=betas,
+                                full_pose=torch.cat([go, bp], dim=1) if return_full_pose else None)
+
+    def _forward_impl(self, betas=None, body_pose=None, global_orient=None, transl=None, return_verts=True,
+                      return_full_pose=False, pose2rot=True, pose6d=None, bodies_per_cta=0):
         dev = self.v_template.device
         if dev.type != "cuda":
             raise RuntimeError("danet_b200.SMPL: move the module to a CUDA device first (no CPU path)")
@@ -309,6 +343,81 @@ class SMPL(nn.Module):
     def joints_h36m(self):
         """[B,17,3] J_regressor_h36m joints of the last forward (eval.py:186,202 fused into the pass)."""
         return self.last_joints_h36m
+
+
+class _SmplLbs(torch.autograd.Function):
+    """vertices, joints (49), smpl_joints = SMPL(betas, rotmats) with the CUDA forward and backward of csrc/lbs.cu.
+    joints = cat[posed skeleton 24 | selected vertices | J_regressor_extra . vertices][joint_map] (models/smpl.py:27-35),
+    so their gradient folds into dL/dposed-joints and dL/dvertices before the LBS backward kernel runs."""
+
+    @staticmethod
+    def forward(ctx, module, betas, rotmats):
+        with torch.no_grad():
+            out = module._forward_impl(betas=betas, body_pose=rotmats[:, 1:], global_orient=rotmats[:, :1], pose2rot=False)
+        ctx.module = module
+        ctx.save_for_backward(betas.detach(), rotmats.detach())
+        return out.vertices, out.joints, out.smpl_joints
+
+    @staticmethod
+    def backward(ctx, g_verts, g_joints, g_smpl_joints):
+        m = ctx.module
+        betas, rotmats = ctx.saved_tensors
+        dev = betas.device
+        B, V = betas.shape[0], m.v_template.shape[0]
+        gv = torch.zeros(B, V, 3, device=dev) if g_verts is None else g_verts.to(torch.float32).clone()
+        gs = torch.zeros(B, 24, 3, device=dev) if g_smpl_joints is None else g_smpl_joints.to(torch.float32).clone()
+        if g_joints is not None:
+            sel = torch.as_tensor(np.asarray(m.selected_verts), dtype=torch.long, device=dev)
+            nsel, nextra = sel.numel(), m.J_regressor_extra.shape[0]
+            gcat = torch.zeros(B, 24 + nsel + nextra, 3, device=dev)
+            gcat.index_add_(1, m.joint_map.to(dev), g_joints.to(torch.float32))
+            gs += gcat[:, :24]
+            gv.index_add_(1, sel, gcat[:, 24:24 + nsel])
+            gv += torch.einsum("jv,bjc->bvc", m.J_regressor_extra.to(dev), gcat[:, 24 + nsel:])
+        gb, gR = m.backward_lbs(betas, rotmats, gv, gs)
+        return None, gb, gR
+
+
+def smpl_losses(smpl, para, target, target_kps, target_kps3d, target_verts, has_kp3d, has_smpl, focal_length=5000.0,
+                img_size=224, openpose_weight=0.0, gt_weight=1.0, weights=None):
+    """The SMPL-branch losses of the reference's training step (models/danet/smpl_regressor.py:170-215 with the
+    criteria of :224-330: keypoint 2D / 3D, per-vertex, pose / betas regression, camera) on top of the differentiable
+    SMPL layer.  para / target [B,229] = cam 3 | betas 10 | 24 rotation matrices; target_kps [B,49,3] (x, y in [-1,1],
+    confidence); target_kps3d [B,24,4]; target_verts [B,6890,3]; has_kp3d / has_smpl [B] masks.  Returns a dict of
+    scalar losses (already multiplied by their weights); the loss arithmetic is plain torch on the GPU -- the SMPL
+    forward / backward underneath are the CUDA kernels."""
+    w = {"keypoints_2d": 300.0, "keypoints_3d": 300.0, "smpl_pose": 60.0, "smpl_betas": 0.06, "smpl_verts": 0.0}      # configs/danet_default.yaml:25-29
+    if weights:
+        w.update(weights)
+    B = para.shape[0]
+    cam, betas, rot = para[:, :3], para[:, 3:13], para[:, 13:].reshape(B, 24, 3, 3)
+    out = smpl(betas=betas, body_pose=rot[:, 1:], global_orient=rot[:, :1], pose2rot=False)
+    verts, joints = out.vertices, out.joints
+    cam_t = torch.stack([cam[:, 1], cam[:, 2], 2 * focal_length / (img_size * cam[:, 0] + 1e-9)], dim=-1)
+    pts = joints + cam_t.unsqueeze(1)                                       # rotation = identity, centre = 0
+    kp2d = focal_length * pts[..., :2] / pts[..., 2:3] / (img_size / 2.0)
+    conf = target_kps[:, :, -1:].clone()
+    conf[:, :25] *= openpose_weight
+    conf[:, 25:] *= gt_weight
+    losses = {"keypoints_2d": w["keypoints_2d"] * (conf * (kp2d - target_kps[:, :, :-1]) ** 2).mean()}
+    sel3 = has_kp3d.bool()
+    if sel3.any():
+        gt3, c3 = target_kps3d[sel3, :, :3], target_kps3d[sel3, :, 3:]
+        pj = joints[sel3][:, 25:]
+        gt3 = gt3 - (gt3[:, 2] + gt3[:, 3]).unsqueeze(1) / 2
+        pj = pj - (pj[:, 2] + pj[:, 3]).unsqueeze(1) / 2
+        losses["keypoints_3d"] = w["keypoints_3d"] * (c3 * (pj - gt3) ** 2).mean()
+    else:
+        losses["keypoints_3d"] = para.sum() * 0
+    sels = has_smpl.bool()
+    if sels.any():
+        losses["smpl_verts"] = w["smpl_verts"] * (verts[sels] - target_verts[sels]).abs().mean()
+        losses["smpl_pose"] = w["smpl_pose"] * ((rot[sels] - target[sels, 13:].reshape(-1, 24, 3, 3)) ** 2).mean()
+        losses["smpl_betas"] = w["smpl_betas"] * ((betas[sels] - target[sels, 3:13]) ** 2).mean()
+    else:
+        losses["smpl_verts"] = losses["smpl_pose"] = losses["smpl_betas"] = para.sum() * 0
+    losses["cam"] = (torch.exp(-cam[:, 0] * 10) ** 2).mean()
+    return losses
 
 
 def save_smpl_npz(path, model):

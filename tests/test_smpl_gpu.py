@@ -164,3 +164,78 @@ def test_smpl_backward_matches_fp64_finite_differences(smpl_model):
     eR = np.abs(gR.cpu().numpy() - gR_fd).max() / sR
     print("LBS backward vs fp64 finite differences: rel err dbeta %.2e dR %.2e" % (eb, eR))
     assert eb < 2e-4 and eR < 2e-4
+
+
+def _oracle_smpl_losses(model, para, target, target_kps, target_kps3d, target_verts, has_kp3d, has_smpl, w,
+                        focal=5000.0, img=224, openpose_weight=0.0, gt_weight=1.0):
+    """fp64 numpy restatement of smpl_regressor.py:170-215 + criteria :248-300 (test infrastructure)."""
+    B = para.shape[0]
+    cam, betas, rot = para[:, :3], para[:, 3:13], para[:, 13:].reshape(B, 24, 3, 3)
+    o = lbs.smpl_forward(model, betas, rot[:, 1:], rot[:, :1], pose2rot=False, dtype=np.float64)
+    verts, joints = o["vertices"], o["joints"]
+    cam_t = np.stack([cam[:, 1], cam[:, 2], 2 * focal / (img * cam[:, 0] + 1e-9)], -1)
+    pts = joints + cam_t[:, None]
+    kp2d = focal * pts[..., :2] / pts[..., 2:3] / (img / 2.0)
+    conf = target_kps[:, :, -1:].copy()
+    conf[:, :25] *= openpose_weight
+    conf[:, 25:] *= gt_weight
+    total = w["keypoints_2d"] * (conf * (kp2d - target_kps[:, :, :-1]) ** 2).mean()
+    s3 = has_kp3d.astype(bool)
+    gt3, c3 = target_kps3d[s3, :, :3], target_kps3d[s3, :, 3:]
+    pj = joints[s3][:, 25:]
+    gt3 = gt3 - ((gt3[:, 2] + gt3[:, 3]) / 2)[:, None]
+    pj = pj - ((pj[:, 2] + pj[:, 3]) / 2)[:, None]
+    total += w["keypoints_3d"] * (c3 * (pj - gt3) ** 2).mean()
+    ss = has_smpl.astype(bool)
+    total += w["smpl_verts"] * np.abs(verts[ss] - target_verts[ss]).mean()
+    total += w["smpl_pose"] * ((rot[ss] - target[ss, 13:].reshape(-1, 24, 3, 3)) ** 2).mean()
+    total += w["smpl_betas"] * ((betas[ss] - target[ss, 3:13]) ** 2).mean()
+    total += (np.exp(-cam[:, 0] * 10) ** 2).mean()
+    return total
+
+
+def test_differentiable_smpl_and_training_losses_match_fp64_finite_differences(smpl_model):
+    """The SMPL branch of the reference's training step (smpl_regressor.py:170-215): losses on top of the differentiable
+    SMPL layer (CUDA forward + danet_smpl_backward through a torch.autograd.Function, including the 49-joint selection /
+    extra-regressor path); d(total loss)/d(para) against central finite differences of an fp64 restatement."""
+    import danet_b200
+    from danet_b200.smpl import smpl_losses
+    dev = torch.device("cuda:0")
+    B = 3
+    rng = np.random.default_rng(7)
+    x6 = rng.normal(0, 1, (B, 24, 6))
+    R = lbs.rot6d_to_rotmat(x6.reshape(-1, 6)).reshape(B, 216)
+    para = np.concatenate([np.stack([rng.uniform(0.6, 1.1, B), rng.normal(0, .05, B), rng.normal(0, .05, B)], 1),
+                           rng.normal(0, 1, (B, 10)), R + rng.normal(0, 0.02, (B, 216))], 1)
+    target = para + rng.normal(0, 0.1, para.shape)
+    kps = np.concatenate([rng.uniform(-1, 1, (B, 49, 2)), rng.uniform(0, 1, (B, 49, 1))], -1)
+    kps3d = np.concatenate([rng.normal(0, .3, (B, 24, 3)), rng.uniform(0, 1, (B, 24, 1))], -1)
+    tverts = rng.normal(0, .5, (B, 6890, 3))
+    has3 = np.array([1, 0, 1]); hass = np.array([1, 1, 0])
+    w = {"keypoints_2d": 3.0, "keypoints_3d": 300.0, "smpl_pose": 60.0, "smpl_betas": 0.06, "smpl_verts": 60.0}
+    smpl = danet_b200.SMPL(smpl_model, batch_size=B).to(dev)
+    t = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float32)).to(dev)
+    p = t(para).requires_grad_(True)
+    losses = smpl_losses(smpl, p, t(target), t(kps), t(kps3d), t(tverts), t(has3), t(hass), weights=w)
+    total = sum(losses.values())
+    total.backward()
+    g = p.grad.cpu().numpy().astype(np.float64)
+    f = lambda pp: _oracle_smpl_losses(smpl_model, pp, target, kps, kps3d, tverts, has3, hass, w)
+    want_total = f(para)
+    assert abs(total.item() - want_total) / abs(want_total) < 1e-4, (total.item(), want_total)
+    idx = [(b, k) for b in range(B) for k in list(range(13)) + list(rng.choice(np.arange(13, 229), 30, replace=False))]
+    eps = 1e-5
+    fd = np.zeros(len(idx)); got = np.zeros(len(idx))
+    for n, (b, k) in enumerate(idx):
+        pp, pm = para.copy(), para.copy()
+        pp[b, k] += eps; pm[b, k] -= eps
+        fd[n] = (f(pp) - f(pm)) / (2 * eps)
+        got[n] = g[b, k]
+    rel = np.abs(got - fd).max() / np.abs(fd).max()
+    print("training-loss gradient vs fp64 finite differences: max rel err %.2e over %d entries" % (rel, len(idx)))
+    assert rel < 5e-4
+    # plain inference calls are untouched (no autograd graph, same numbers)
+    with torch.no_grad():
+        o = smpl(betas=p[:, 3:13], body_pose=p[:, 13:].reshape(B, 24, 3, 3)[:, 1:], global_orient=p[:, 13:].reshape(B, 24, 3, 3)[:, :1],
+                 pose2rot=False)
+    assert not o.vertices.requires_grad

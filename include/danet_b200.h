@@ -263,7 +263,8 @@ int danet_gcn_pose_head(int32_t B, const danet_gcn_params* p, const float* rot_f
  * A "network program" is what danet_b200.plan.Plan.export() writes for ONE batch size: the launch steps (each one of
  * the entries above, with its arguments), the activation buffer table and the BN-folded, packed weights.  Loading
  * allocates everything on the CURRENT device; infer replays the steps (optionally as one CUDA graph, captured on the
- * first call).  Outputs stay in the program's buffers until the next infer:
+ * first call).  A danet_net_t owns its buffers: one infer at a time per handle (load one handle per host thread / stream
+ * that runs concurrently).  Outputs stay in the program's buffers until the next infer:
  *   "para" [B,229] f32 (cam 3 | shape 10 | 24 rotation matrices, danet.py:118), "centers" [B,24,2] (stn_kps_pred),
  *   "theta", "global_para", "rot_feats", "heads", "hm", "body_iuv", "amax" (u8 [B,S,S]) and, when the plan kept the
  *   visualisation maps, "vis_u" / "vis_v" / "vis_i" [B,25,S,S], "vis_a" [B,15,S,S], "part_iuv_raw" [B*24,21,S,S].

@@ -336,47 +336,65 @@ k_stn_sample(int B, int S, int C, ActV xd, const float* __restrict__ theta,
 // ------------------------------------------------------------------------------------------
 struct FuseArgs { ActV t[4]; int f[4]; int n; };      // f = log2 of the upsample factor (1,2,4,8 -> 0..3)
 
-// grid = (n*H + h, chunks of a row): no per-element 64-bit division
+// grid = (n*H + h, chunks of a row): no per-element 64-bit division.  V = channels per thread (8: 16-byte plane accesses)
+template <int V>
 __global__ void __launch_bounds__(256)
-k_fuse_sum(int N, int H, int W, int C4, unsigned long long mC4, FuseArgs a, int relu, ActV y) {
+k_fuse_sum(int N, int H, int W, int CV, unsigned long long mCV, FuseArgs a, int relu, ActV y) {
     const int row = blockIdx.x;
     const int n = row / H, h = row - n * H;
     const int i = blockIdx.y * blockDim.x + threadIdx.x;
-    if (i >= W * C4) return;
-    const int w = (int)(((unsigned long long)(unsigned)i * mC4) >> 40), c4 = i - w * C4;     // i / C4, exact (i < 2^24)
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i >= W * CV) return;
+    const int w = (int)(((unsigned long long)(unsigned)i * mCV) >> 40), cv = i - w * CV;     // i / CV, exact (i < 2^24)
+    float acc[V];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         if (j >= a.n) break;
         const int sh = a.f[j];
-        const float4 v = act_ld4(a.t[j], (((size_t)(n * (H >> sh) + (h >> sh)) * (W >> sh) + (w >> sh)) * C4 + c4) * 4);
-        if (j == 0) acc = v;
-        else { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+        const size_t e = (((size_t)(n * (H >> sh) + (h >> sh)) * (W >> sh) + (w >> sh)) * CV + cv) * V;
+        float v[V];
+        if (V == 8) { const float8 t = act_ld8(a.t[j], e); v[0] = t.a.x; v[1] = t.a.y; v[2] = t.a.z; v[3] = t.a.w; v[4 % V] = t.b.x; v[5 % V] = t.b.y; v[6 % V] = t.b.z; v[7 % V] = t.b.w; }
+        else { const float4 t = act_ld4(a.t[j], e); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] = (j == 0) ? v[k] : acc[k] + v[k];
     }
-    if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
-    act_st4(y, ((size_t)row * W * C4 + i) * 4, acc);
+    if (relu) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] = fmaxf(acc[k], 0.f);
+    }
+    const size_t o = ((size_t)row * W * CV + i) * V;
+    if (V == 8) { float8 t; t.a = make_float4(acc[0], acc[1], acc[2], acc[3]); t.b = make_float4(acc[4 % V], acc[5 % V], acc[6 % V], acc[7 % V]); act_st8(y, o, t); }
+    else act_st4(y, o, make_float4(acc[0], acc[1], acc[2], acc[3]));
 }
 
+template <int V>
 __global__ void __launch_bounds__(256)
-k_maxpool3x3s2(int N, int H, int W, int C4, ActV x, ActV y) {
+k_maxpool3x3s2(int N, int H, int W, int CV, ActV x, ActV y) {
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
     const int row = blockIdx.x;
     const int n = row / Ho, ho = row - n * Ho;
     const int i = blockIdx.y * blockDim.x + threadIdx.x;
-    if (i >= Wo * C4) return;
-    const int wo = i / C4, c4 = i - wo * C4;
-    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    if (i >= Wo * CV) return;
+    const int wo = i / CV, cv = i - wo * CV;
+    float m[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) m[k] = -INFINITY;
     for (int dy = 0; dy < 3; ++dy) {
         const int hh = ho * 2 - 1 + dy;
         if (hh < 0 || hh >= H) continue;
         for (int dx = 0; dx < 3; ++dx) {
             const int ww = wo * 2 - 1 + dx;
             if (ww < 0 || ww >= W) continue;
-            const float4 v = act_ld4(x, (((size_t)(n * H + hh) * W + ww) * C4 + c4) * 4);
-            m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+            const size_t e = (((size_t)(n * H + hh) * W + ww) * CV + cv) * V;
+            float v[V];
+            if (V == 8) { const float8 t = act_ld8(x, e); v[0] = t.a.x; v[1] = t.a.y; v[2] = t.a.z; v[3] = t.a.w; v[4 % V] = t.b.x; v[5 % V] = t.b.y; v[6 % V] = t.b.z; v[7 % V] = t.b.w; }
+            else { const float4 t = act_ld4(x, e); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+#pragma unroll
+            for (int k = 0; k < V; ++k) m[k] = fmaxf(m[k], v[k]);
         }
     }
-    act_st4(y, ((size_t)row * Wo * C4 + i) * 4, m);
+    const size_t o = ((size_t)row * Wo * CV + i) * V;
+    if (V == 8) { float8 t; t.a = make_float4(m[0], m[1], m[2], m[3]); t.b = make_float4(m[4 % V], m[5 % V], m[6 % V], m[7 % V]); act_st8(y, o, t); }
+    else act_st4(y, o, make_float4(m[0], m[1], m[2], m[3]));
 }
 
 __global__ void k_global_avgpool(int N, int HW, int C, ActV x, float* __restrict__ y) {
@@ -678,7 +696,10 @@ extern "C" int danet_fuse_sum(int32_t N, int32_t H, int32_t W, int32_t C, int32_
         a.t[j] = actv(&terms[j]); a.f[j] = f == 1 ? 0 : (f == 2 ? 1 : (f == 4 ? 2 : 3));
     }
     DANET_CHECK((int64_t)N * H < (1LL << 31) && (int64_t)W * (C / 4) < (1 << 24) && C / 4 < (1 << 16), "danet_fuse_sum: tensor too large for one launch");
-    k_fuse_sum<<<dim3(N * H, cdiv(W * (C / 4), 256)), 256, 0, (cudaStream_t)s>>>(N, H, W, C / 4, (1ull << 40) / (unsigned long long)(C / 4) + 1ull, a, relu, actv(y));
+    if (C % 8 == 0)
+        k_fuse_sum<8><<<dim3(N * H, cdiv(W * (C / 8), 256)), 256, 0, (cudaStream_t)s>>>(N, H, W, C / 8, (1ull << 40) / (unsigned long long)(C / 8) + 1ull, a, relu, actv(y));
+    else
+        k_fuse_sum<4><<<dim3(N * H, cdiv(W * (C / 4), 256)), 256, 0, (cudaStream_t)s>>>(N, H, W, C / 4, (1ull << 40) / (unsigned long long)(C / 4) + 1ull, a, relu, actv(y));
     DANET_LAUNCH_CHECK();
     return 0;
 }
@@ -689,7 +710,8 @@ extern "C" int danet_maxpool3x3s2(int32_t N, int32_t H, int32_t W, int32_t C, co
     if (check_act(x, "danet_maxpool3x3s2(x)", false, C) != 0 || check_act(y, "danet_maxpool3x3s2(y)", false, C) != 0) return -1;
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
     DANET_CHECK((int64_t)N * Ho < (1LL << 31) && (int64_t)Wo * (C / 4) <= 65535LL * 256, "danet_maxpool3x3s2: tensor too large for one launch");
-    k_maxpool3x3s2<<<dim3(N * Ho, cdiv(Wo * (C / 4), 256)), 256, 0, (cudaStream_t)s>>>(N, H, W, C / 4, actv(x), actv(y));
+    if (C % 8 == 0) k_maxpool3x3s2<8><<<dim3(N * Ho, cdiv(Wo * (C / 8), 256)), 256, 0, (cudaStream_t)s>>>(N, H, W, C / 8, actv(x), actv(y));
+    else k_maxpool3x3s2<4><<<dim3(N * Ho, cdiv(Wo * (C / 4), 256)), 256, 0, (cudaStream_t)s>>>(N, H, W, C / 4, actv(x), actv(y));
     DANET_LAUNCH_CHECK();
     return 0;
 }

@@ -423,6 +423,7 @@ __global__ void k_linear(int N, int In, int Out, const float* __restrict__ x, co
 // ------------------------------------------------------------------------------------------
 constexpr int kGcnThreads = 256;
 constexpr int kGcnMaxF = 256;
+constexpr int kGcnTF = 32;                 // input features per streamed weight tile
 
 struct GcnArgs {
     const float* adj;
@@ -453,6 +454,7 @@ k_gcn_pose_head(int B, GcnArgs g, const float* __restrict__ rot_feats, const flo
     float* s_res = s_gcn + 2 * 24 * kGcnMaxF;    // [24][128] residual (pos_feats_init)
     float* s_adj = s_res + 24 * 128;             // [24][24]
     float* s_p6 = s_adj + 576;                   // [144]
+    float* s_W = s_p6 + 144;                     // [2][kGcnTF][<= kGcnMaxF] streamed weight tiles (16-byte aligned: all sizes above are multiples of 4 floats)
     const int b = blockIdx.x, tid = threadIdx.x;
     for (int i = tid; i < 24 * 128; i += kGcnThreads) s_x[(i / 128) * kGcnMaxF + (i % 128)] = rot_feats[(size_t)b * 24 * 128 + i];
     __syncthreads();
@@ -470,25 +472,44 @@ k_gcn_pose_head(int B, GcnArgs g, const float* __restrict__ rot_feats, const flo
             s_ax[n * kGcnMaxF + f] = s;
         }
         __syncthreads();
-        // y = relu(bn(ax @ W + b)); thread tid owns column o = tid
-        if (tid < Fo) {
-            float acc[24];
+        // y = relu(bn(ax @ W + b)); thread tid owns column o = tid.  W streams through shared memory in tiles of kGcnTF input
+        // features (cp.async, double-buffered, all 256 threads, coalesced): the per-thread column walk it replaces waited
+        // one L2 round trip per 4 features (33 us per layer, latency-bound)
+        const float* W = g.W[l];
+        const int ntile = (F + kGcnTF - 1) / kGcnTF;
+        auto fetch = [&](int t) {
+            const int f0 = t * kGcnTF, nf = min(kGcnTF, F - f0);
+            const float* src = W + (size_t)f0 * Fo;
+            float* dst = s_W + (t & 1) * kGcnTF * kGcnMaxF;
+            for (int i4 = tid; i4 < nf * Fo / 4; i4 += kGcnThreads) {
+                const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + 4 * i4);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + 4 * i4) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        float acc[24];
 #pragma unroll
-            for (int n = 0; n < 24; ++n) acc[n] = 0.f;
-            const float* W = g.W[l];
-            // 4 input features per step: 4 independent weight loads in flight and one 16-byte
-            // broadcast smem read per node instead of four scalar ones (the loop was LDS-bound)
-            // (unrolled x4: 16 weight loads in flight -- one L2 round trip per 16 input features instead of per 4)
-#pragma unroll 4
-            for (int f = 0; f < F; f += 4) {
-                const float w0 = __ldg(W + (size_t)f * Fo + tid), w1 = __ldg(W + (size_t)(f + 1) * Fo + tid);
-                const float w2 = __ldg(W + (size_t)(f + 2) * Fo + tid), w3 = __ldg(W + (size_t)(f + 3) * Fo + tid);
+        for (int n = 0; n < 24; ++n) acc[n] = 0.f;
+        fetch(0);
+        for (int t = 0; t < ntile; ++t) {
+            if (t + 1 < ntile) { fetch(t + 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();
+            if (tid < Fo) {
+                const float* sw = s_W + (t & 1) * kGcnTF * kGcnMaxF;
+                const int f0 = t * kGcnTF, nf = min(kGcnTF, F - f0);
+                for (int ff = 0; ff < nf; ff += 4) {
+                    const float w0 = sw[ff * Fo + tid], w1 = sw[(ff + 1) * Fo + tid], w2 = sw[(ff + 2) * Fo + tid], w3 = sw[(ff + 3) * Fo + tid];
 #pragma unroll
-                for (int n = 0; n < 24; ++n) {
-                    const float4 av = *reinterpret_cast<const float4*>(&s_ax[n * kGcnMaxF + f]);
-                    acc[n] = fmaf(av.x, w0, fmaf(av.y, w1, fmaf(av.z, w2, fmaf(av.w, w3, acc[n]))));
+                    for (int n = 0; n < 24; ++n) {
+                        const float4 av = *reinterpret_cast<const float4*>(&s_ax[n * kGcnMaxF + f0 + ff]);
+                        acc[n] = fmaf(av.x, w0, fmaf(av.y, w1, fmaf(av.z, w2, fmaf(av.w, w3, acc[n]))));
+                    }
                 }
             }
+            __syncthreads();                                   // the buffer is refilled two tiles later
+        }
+        if (tid < Fo) {
             const float bias = g.b[l][tid];
 #pragma unroll
             for (int n = 0; n < 24; ++n) {
@@ -747,14 +768,14 @@ extern "C" int danet_gcn_pose_head(int32_t B, const danet_gcn_params* p, const f
     for (int l = 0; l < 5; ++l) {
         DANET_CHECK(p->W[l] && p->b[l] && p->bn_scale[l] && p->bn_shift[l], "danet_gcn_pose_head: layer %d has null params", l);
         DANET_CHECK(p->dim_in[l] > 0 && p->dim_in[l] <= kGcnMaxF && p->dim_out[l] > 0 && p->dim_out[l] <= kGcnMaxF &&
-                    p->dim_in[l] % 4 == 0,
-                    "danet_gcn_pose_head: layer %d dims %d->%d must be <= %d and the input a multiple of 4", l, p->dim_in[l], p->dim_out[l], kGcnMaxF);
+                    p->dim_in[l] % 4 == 0 && p->dim_out[l] % 4 == 0 && ((uintptr_t)p->W[l] & 15) == 0,
+                    "danet_gcn_pose_head: layer %d dims %d->%d must be <= %d, multiples of 4, W 16-byte aligned", l, p->dim_in[l], p->dim_out[l], kGcnMaxF);
         g.W[l] = p->W[l]; g.b[l] = p->b[l]; g.bn_s[l] = p->bn_scale[l]; g.bn_t[l] = p->bn_shift[l];
         g.din[l] = p->dim_in[l]; g.dout[l] = p->dim_out[l];
     }
     DANET_CHECK(g.din[0] == 128 && g.dout[0] == 128 && g.dout[3] == 128 && g.din[4] == 128 && g.dout[4] == 128,
                 "danet_gcn_pose_head: expected 128-d r2p / refine-out / p2r features");
-    const size_t smem = (size_t)(2 * 24 * kGcnMaxF + 24 * 128 + 576 + 144) * sizeof(float);
+    const size_t smem = (size_t)(2 * 24 * kGcnMaxF + 24 * 128 + 576 + 144 + 2 * kGcnTF * kGcnMaxF) * sizeof(float);
     static unsigned long long attr_devs = 0;
     if (first_use_on_current_device(&attr_devs) != 0)
         DANET_CUDA(cudaFuncSetAttribute(k_gcn_pose_head, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -143,6 +143,7 @@ class DaNet(nn.Module):
 
     # -- plan cache -----------------------------------------------------------------------------
     MAX_PLANS = 4                                      # batch sizes kept compiled (LRU)
+    MAX_BATCH = 256                                    # images per plan; larger batches are chunked (infer_net)
 
     def _invalidate(self):
         self._plans = {}
@@ -215,6 +216,26 @@ class DaNet(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("danet_b200.DaNet: move the model to a CUDA device (there is no CPU path)")
         B = image.shape[0]
+        S = self.cfg["HEATMAP_SIZE"]
+        if B == 0:                                       # what the reference's modules return for an empty batch
+            z = lambda *shape: torch.zeros(*shape, device=dev)
+            vis = {"iuv_pred": [z(0, c, S, S) for c in (25, 25, 25, 15)], "part_iuv_pred": z(0, 24, 3, 7, S, S)} if self.want_vis else {}
+            return {"para": z(0, 229), "visualization": vis, "stn_kps_pred": z(0, 24, 2)}
+        if B > self.MAX_BATCH:
+            # the kernels index activations with 32-bit element offsets (the 24 x B part crops are the largest tensor):
+            # larger batches run as chunks; their visualisation maps are copied (a plan's buffers are reused per chunk)
+            outs = []
+            for lo in range(0, B, self.MAX_BATCH):
+                o = self.infer_net(image[lo:lo + self.MAX_BATCH])
+                o["visualization"] = {k: ([t.clone() for t in v] if isinstance(v, list) else v.clone())
+                                      for k, v in o["visualization"].items()}
+                outs.append(o)
+            ret = {"para": torch.cat([o["para"] for o in outs]), "stn_kps_pred": torch.cat([o["stn_kps_pred"] for o in outs]),
+                   "visualization": {}}
+            if self.want_vis:
+                ret["visualization"]["iuv_pred"] = [torch.cat([o["visualization"]["iuv_pred"][i] for o in outs]) for i in range(4)]
+                ret["visualization"]["part_iuv_pred"] = torch.cat([o["visualization"]["part_iuv_pred"] for o in outs])
+            return ret
         plan = self.plan_for(B, dev)
         plan.run(image)
         return self.outputs_of(plan, B)

@@ -96,6 +96,9 @@ class IUV_Renderer(object):
         verts_c = verts.detach().float().contiguous()
         cam_c = cam.detach().to(dev).float().contiguous()
         S = self.out_size
+        if B == 0:                                       # empty batch: empty outputs, nothing to launch
+            return (torch.empty(0, 3, S, S, device=dev), torch.empty(0, S, S, dtype=torch.int32, device=dev) if want_face_idx else None,
+                    [torch.empty(0, c, S, S, device=dev) for c in (25, 25, 25, 15)] if want_maps else [None] * 4)
         lib = _lib.load()
         with torch.cuda.device(dev):
             h = self._handle(dev)

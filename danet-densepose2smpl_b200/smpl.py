@@ -282,6 +282,13 @@ class SMPL(nn.Module):
             go_in, bp_in = go, bp
         if betas.shape[0] != B or pose.shape[0] != B:
             raise ValueError("SMPL.forward: inconsistent batch sizes")
+        if B == 0:                                       # empty batch: empty outputs of the usual shapes, nothing to launch
+            z = lambda *shape: torch.zeros(*shape, device=dev)
+            self.last_joints_h36m = None if self.J_regressor_h36m is None else z(0, self.J_regressor_h36m.shape[0], 3)
+            self.last_rotmats = z(0, 24, 3, 3)
+            return self.ModelOutput(vertices=z(0, self.v_template.shape[0], 3) if return_verts else None, global_orient=go_in,
+                                    body_pose=bp_in, joints=z(0, len(self.joint_map), 3), joints_J19=z(0, 19, 3),
+                                    smpl_joints=z(0, 24, 3), betas=betas, full_pose=None)
         lib = _lib.load()
         with torch.cuda.device(dev):
             h = self._handle(dev)

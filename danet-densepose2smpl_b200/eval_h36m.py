@@ -89,24 +89,24 @@ def run_evaluation(model, dataset_name, dataset, result_file=None, batch_size=32
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
+    j17 = dataset_name == "mpi-inf-3dhp"                    # eval.py:139-140: 17 joints there, the 14 LSP joints otherwise
     if batch_fn is None:
         dev = next(model.parameters()).device
         smpl = model.iuv2smpl.smpl
-        batch_fn = lambda im, gt: evaluate_batch(model, smpl, im.to(dev), gt.to(dev), shard=False)
+        batch_fn = lambda im, gt: evaluate_batch(model, smpl, im.to(dev), gt.to(dev), shard=False, joints17=j17)
     else:
         dev = torch.device("cpu")
-    if dataset_name == "mpi-inf-3dhp":
-        raise NotImplementedError("the fused H36M-joint pass selects the 14 LSP joints (h36m-p1/p2); mpi-inf-3dhp uses 17")
+    nj = 17 if j17 else 14
     n = len(dataset)
     nb = (n + batch_size - 1) // batch_size
     mpjpe = np.zeros(n)
     recon = np.zeros(n)
     done = np.zeros(n, dtype=bool)
-    pred_joints = np.zeros((n, 14, 3), dtype=np.float32)
+    pred_joints = np.zeros((n, nj, 3), dtype=np.float32)
     for b in range(rank, nb, world):
         lo, hi = b * batch_size, min(n, (b + 1) * batch_size)
         img, pose_3d = dataset.batch(lo, hi)
-        gt = torch.from_numpy(pose_3d[:, constants.J24_TO_J14, :3].copy())          # eval.py:196-200
+        gt = torch.from_numpy(pose_3d[:, constants.J24_TO_J17 if j17 else constants.J24_TO_J14, :3].copy())     # eval.py:189-190
         out = batch_fn(img, gt)                              # this rank's batch only (the loop deals the batches)
         e = out["mpjpe"].cpu().numpy()
         pj = out["pred_j14"].cpu().numpy()
@@ -151,7 +151,7 @@ def run_evaluation(model, dataset_name, dataset, result_file=None, batch_size=32
 def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__.split("\n")[0])
     ap.add_argument("--checkpoint", default=None, help="path to the network checkpoint (the reference's .pt with a 'model' entry)")
-    ap.add_argument("--dataset", default="h36m-p2", choices=["h36m-p1", "h36m-p2"])
+    ap.add_argument("--dataset", default="h36m-p2", choices=["h36m-p1", "h36m-p2", "mpi-inf-3dhp"])
     ap.add_argument("--cache", required=True, help="npz with img / pose_3d / imgname (see module docstring)")
     ap.add_argument("--batch_size", default=32, type=int)
     ap.add_argument("--log_freq", default=50, type=int)

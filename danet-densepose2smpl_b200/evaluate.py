@@ -17,7 +17,7 @@ from .smpl import mpjpe_h36m
 
 
 @torch.no_grad()
-def evaluate_batch(model, smpl, images, gt_keypoints_3d_j14, group=None, shard=True):
+def evaluate_batch(model, smpl, images, gt_keypoints_3d_j14, group=None, shard=True, joints17=False):
     """images [N,3,224,224]; gt_keypoints_3d_j14 [N,14,3] (pelvis-centred H36M joints in the
     H36M_TO_J14 order, eval.py:196-200).  Returns dict(mpjpe [N] in metres, pred_j14 [N,14,3],
     para [N,229]) on every rank.  shard=False: evaluate all N images on this rank, no collective
@@ -35,12 +35,18 @@ def evaluate_batch(model, smpl, images, gt_keypoints_3d_j14, group=None, shard=T
         j17 = smpl.joints_h36m()
         if j17 is None:
             raise ValueError("evaluate_batch: the SMPL layer was built without J_regressor_h36m (eval.py:78)")
-        err = mpjpe_h36m(j17, gt_keypoints_3d_j14[lo:hi].to(dev))
-        j14 = (j17 - j17[:, :1])[:, constants.H36M_TO_J14]
+        if joints17:
+            # mpi-inf-3dhp (eval.py:139-140): all 17 H36M joints; gt is [N,17,3] in the J24_TO_J17 order.  Same expressions
+            # as eval.py:202-211, in torch on the GPU (the fused kernel selects the 14 LSP joints)
+            j14 = (j17 - j17[:, :1])[:, constants.H36M_TO_J17]
+            err = torch.sqrt(((j14 - gt_keypoints_3d_j14[lo:hi].to(dev)) ** 2).sum(dim=-1)).mean(dim=-1)
+        else:
+            err = mpjpe_h36m(j17, gt_keypoints_3d_j14[lo:hi].to(dev))
+            j14 = (j17 - j17[:, :1])[:, constants.H36M_TO_J14]
     else:
         para = torch.zeros(0, 229, device=dev)
         err = torch.zeros(0, device=dev)
-        j14 = torch.zeros(0, 14, 3, device=dev)
+        j14 = torch.zeros(0, 17 if joints17 else 14, 3, device=dev)
     if world == 1:
         return {"mpjpe": err, "pred_j14": j14, "para": para}
     return {"mpjpe": gather_outputs(err, n, group), "pred_j14": gather_outputs(j14, n, group),

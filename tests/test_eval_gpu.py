@@ -70,3 +70,21 @@ def test_eval_loop_two_gpus_equals_one(tmp_path):
     # images are independent and the tensor-core path is batch-invariant: dealing batches to two GPUs changes nothing
     np.testing.assert_array_equal(got["mpjpe"], want["mpjpe"])
     np.testing.assert_array_equal(got["pred_joints"], want["pred_joints"])
+
+
+def test_eval_loop_mpi_inf_3dhp_uses_17_joints():
+    """eval.py:139-140,189-211 for mpi-inf-3dhp: H36M_TO_J17 / J24_TO_J17, torch path; against the oracle chain."""
+    from danet_b200 import constants, eval_h36m
+    from oracle import lbs, synth
+    net = build(32, "cuda:0", conv_algo="auto")
+    data = _dataset(48)
+    res = eval_h36m.run_evaluation(net, "mpi-inf-3dhp", eval_h36m.CachedPoseDataset(data), batch_size=16, quiet=True)
+    assert res["pred_joints"].shape == (48, 17, 3) and not res["per_action"]
+    para = np.concatenate([net.infer_net(torch.from_numpy(data["img"][lo:lo + 16]).cuda())["para"].cpu().numpy() for lo in range(0, 48, 16)])
+    R = para[:, 13:].reshape(-1, 24, 3, 3)
+    ref = lbs.smpl_forward(synth.make_smpl_model(0), para[:, 3:13], R[:, 1:], R[:, :1], pose2rot=False, dtype=np.float64)
+    jh = ref["joints_h36m"]
+    pred = (jh - jh[:, :1])[:, constants.H36M_TO_J17]
+    gt = data["pose_3d"][:, constants.J24_TO_J17, :3].astype(np.float64)
+    want = np.sqrt(((pred - gt) ** 2).sum(-1)).mean(-1)
+    np.testing.assert_allclose(res["mpjpe"], want, atol=1e-5)

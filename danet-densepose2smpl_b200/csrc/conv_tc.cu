@@ -569,7 +569,7 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
                         tc_fence_after();
                         const uint64_t bd = bd0 + ((sB + bs * a.b_slot_bytes) >> 4);
                         if (elect_one()) {
-                            for (int tt = 0; tt < ((a.variant & 4) ? 0 : ntk); ++tt) {
+                            for (int tt = 0; tt < ((PROF && (a.variant & 4)) ? 0 : ntk); ++tt) {
                                 const uint32_t toff = (uint32_t)P.tapoff16[slot][k0 + tt];
                                 for (int kk = 0; kk < kv; ++kk) {
                                     const uint64_t bdk = bd + tt * tap16 + 2 * kk;
@@ -625,7 +625,7 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
         const int prow = 4 * q + (lane >> 3), pcol = lane & 7;    // this thread's pixel inside the sub-tile
         uint32_t fph = 0; int tog = 0;
         int pi = 0;
-        const bool do_store = !(a.variant & 1);
+        const bool do_store = !(PROF && (a.variant & 1));          // knock-outs live in the profiling instantiation only
         const bool pon = PROF && a.prof != nullptr && blockIdx.x == 0 && warp == 0 && lane == 0;
         long long pwf = 0, pws = 0, pinit = 0, pseg = 0, pst = 0; const long long pt0 = clock64();
         pdl_wait();                                              // residual reads / output writes
@@ -643,8 +643,8 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
             const int NT = P.NT, ACC = P.ACC, S = P.S, nseg = P.nseg, nconcat = P.nconcat, relu = P.relu, big = P.big;
             const int Cout = P.Cout, Wo = P.Wo, Ho = P.Ho;
             const float* __restrict__ bias = P.bias;
-            const float* __restrict__ res_f = (a.variant & 2) ? nullptr : P.res_f;
-            const __half* __restrict__ res_hi = (a.variant & 2) ? nullptr : P.res_hi;
+            const float* __restrict__ res_f = (PROF && (a.variant & 2)) ? nullptr : P.res_f;
+            const __half* __restrict__ res_hi = (PROF && (a.variant & 2)) ? nullptr : P.res_hi;
             const __half* __restrict__ res_lo = P.res_lo;
             float* __restrict__ y_f = P.y_f; __half* __restrict__ y_hi = P.y_hi; __half* __restrict__ y_lo = P.y_lo;
             // the packed weights carry a power-of-two scale 2^s (so that their lo halves are normal fp16 numbers): bias and
@@ -1051,7 +1051,7 @@ int conv_tc_group_launch(int n, const danet_conv_problem* probs, cudaStream_t st
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = g_use_pdl ? 1 : 0;
-    if (a.prof) { DANET_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<true>, a)); }
+    if (a.prof || a.variant) { DANET_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<true>, a)); }      // instrumentation / knock-outs: the profiling instantiation
     else { DANET_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<false>, a)); }
     DANET_LAUNCH_CHECK();
     return 0;

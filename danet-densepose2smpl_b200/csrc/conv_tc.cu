@@ -378,7 +378,10 @@ __device__ __forceinline__ void st_global_v8(float* p, const float* v) {
                  "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
 }
 
-template <bool PROF>
+// EX: precision mode fixed at compile time (1 = every problem of the launch is exact, 0 = every problem is fast, -1 = read
+// it per problem).  The mode-specific instantiations drop the other mode's branches from every role's loop: this kernel
+// is sensitive to its instruction footprint (three knock-out branches were worth 2 % of the step).
+template <bool PROF, int EX>
 __global__ void __launch_bounds__(kThreads, 1)
 k_conv_tc(const __grid_constant__ ArgsN a) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -403,7 +406,7 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
         for (int i = 0; i < kSchedDepth; ++i) { mbar_init(bar_sched_full + 8 * i, 1); mbar_init(bar_sched_empty + 8 * i, kSchedConsumers); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == kWarpA && lane < a.nprob) { tma_prefetch_desc(&a.p[lane].tm[0]); if (a.p[lane].exact) tma_prefetch_desc(&a.p[lane].tm[1]); }
+    if (warp == kWarpA && lane < a.nprob) { tma_prefetch_desc(&a.p[lane].tm[0]); if (EX < 0 ? a.p[lane].exact : EX) tma_prefetch_desc(&a.p[lane].tm[1]); }
     if (warp == kWarpMma) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot_addr), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -450,7 +453,7 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
                 const int h0 = tc.th * kTileH * P.stride - P.pad, w0 = tc.tw * kTileW * P.S * P.stride - P.pad;
                 for (int c = 0; c < P.nchunks; ++c)
                     for (int slot = 0; slot < P.npa; ++slot)
-                        for (int pl = 0; pl <= P.exact; ++pl) {
+                        for (int pl = 0; pl <= (EX < 0 ? P.exact : EX); ++pl) {
                             mbar_wait_t(bar_a_empty + 8 * as, ((aph >> as) & 1u) ^ 1u, pon, &pw);
                             if (P.nstack > 1) {
                                 const uint32_t box_bytes = (uint32_t)(P.box_h * P.sbo_a[slot]);
@@ -516,7 +519,8 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
             while (tile >= a.p[pi].tile_base + a.p[pi].tile_count) ++pi;
             const Prob& P = a.p[pi];
             const TileCoord tc = decode_tile(P, tile - P.tile_base);
-            const int exact = P.exact, big = P.big, lseg = P.lseg, nchunks = P.nchunks, npa = P.npa, TG = P.TG, SWB = P.SWB;
+            const int exact = EX < 0 ? P.exact : EX, big = EX == 1 ? 0 : P.big;      // exact mode never takes both accumulator halves
+            const int lseg = P.lseg, nchunks = P.nchunks, npa = P.npa, TG = P.TG, SWB = P.SWB;
             // the second sub-tile of the last tile column may lie wholly outside the image: its MMAs are skipped
             const bool S2 = P.S == 2 && (tc.tw * 2 + 1) * kTileW < P.Wo;
             const uint32_t ACC = (uint32_t)P.ACC, NT = (uint32_t)P.NT;
@@ -640,7 +644,8 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
             while (tile >= a.p[pi].tile_base + a.p[pi].tile_count) ++pi;
             const Prob& P = a.p[pi];
             const TileCoord tc = decode_tile(P, tile - P.tile_base);
-            const int NT = P.NT, ACC = P.ACC, S = P.S, nseg = P.nseg, nconcat = P.nconcat, relu = P.relu, big = P.big;
+            const int NT = P.NT, ACC = P.ACC, S = P.S, nseg = P.nseg, relu = P.relu;
+            const int nconcat = EX < 0 ? P.nconcat : EX, big = EX == 1 ? 0 : P.big;
             const int Cout = P.Cout, Wo = P.Wo, Ho = P.Ho;
             const float* __restrict__ bias = P.bias;
             const float* __restrict__ res_f = (PROF && (a.variant & 2)) ? nullptr : P.res_f;
@@ -1031,8 +1036,9 @@ int conv_tc_group_launch(int n, const danet_conv_problem* probs, cudaStream_t st
         std::lock_guard<std::mutex> lk(g_tc_mu);
         if (first_use_on_current_device(&g_tc_devs) != 0) {          // function attributes are per device
             DANET_CUDA(cudaDeviceGetAttribute(&g_sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
-            DANET_CUDA(cudaFuncSetAttribute(k_conv_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-            DANET_CUDA(cudaFuncSetAttribute(k_conv_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+            DANET_CUDA(cudaFuncSetAttribute(k_conv_tc<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+            DANET_CUDA(cudaFuncSetAttribute(k_conv_tc<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+            DANET_CUDA(cudaFuncSetAttribute(k_conv_tc<true, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
             g_use_pdl = env_int("DANET_TC_PDL", 1) != 0;
             DANET_CUDA(cudaMalloc((void**)&g_sched[dev], kSchedSlots * 2 * sizeof(unsigned)));
             DANET_CUDA(cudaMemset(g_sched[dev], 0, kSchedSlots * 2 * sizeof(unsigned)));
@@ -1051,8 +1057,15 @@ int conv_tc_group_launch(int n, const danet_conv_problem* probs, cudaStream_t st
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = g_use_pdl ? 1 : 0;
-    if (a.prof || a.variant) { DANET_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<true>, a)); }      // instrumentation / knock-outs: the profiling instantiation
-    else { DANET_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<false>, a)); }
+    int n_exact = 0, n_big = 0;
+    for (int i = 0; i < a.nprob; ++i) { n_exact += a.p[i].exact; n_big += a.p[i].big; }
+    if (a.prof || a.variant || (n_exact != 0 && (n_exact != a.nprob || n_big != 0))) {
+        DANET_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<true, -1>, a));      // instrumentation / knock-outs / mixed modes: the generic instantiation
+    } else if (n_exact) {
+        DANET_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<false, 1>, a));
+    } else {
+        DANET_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<false, 0>, a));
+    }
     DANET_LAUNCH_CHECK();
     return 0;
 }

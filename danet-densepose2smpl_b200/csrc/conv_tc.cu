@@ -381,7 +381,8 @@ __device__ __forceinline__ void st_global_v8(float* p, const float* v) {
 // EX: precision mode fixed at compile time (1 = every problem of the launch is exact, 0 = every problem is fast, -1 = read
 // it per problem).  The mode-specific instantiations drop the other mode's branches from every role's loop: this kernel
 // is sensitive to its instruction footprint (three knock-out branches were worth 2 % of the step).
-template <bool PROF, int EX>
+// RESF: some problem of the launch adds an fp32 residual view (else that path is not compiled in).
+template <bool PROF, int EX, bool RESF>
 __global__ void __launch_bounds__(kThreads, 1)
 k_conv_tc(const __grid_constant__ ArgsN a) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -648,7 +649,7 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
             const int nconcat = EX < 0 ? P.nconcat : EX, big = EX == 1 ? 0 : P.big;
             const int Cout = P.Cout, Wo = P.Wo, Ho = P.Ho;
             const float* __restrict__ bias = P.bias;
-            const float* __restrict__ res_f = (PROF && (a.variant & 2)) ? nullptr : P.res_f;
+            const float* __restrict__ res_f = (!RESF || (PROF && (a.variant & 2))) ? nullptr : P.res_f;
             const __half* __restrict__ res_hi = (PROF && (a.variant & 2)) ? nullptr : P.res_hi;
             const __half* __restrict__ res_lo = P.res_lo;
             float* __restrict__ y_f = P.y_f; __half* __restrict__ y_hi = P.y_hi; __half* __restrict__ y_lo = P.y_lo;
@@ -1036,9 +1037,11 @@ int conv_tc_group_launch(int n, const danet_conv_problem* probs, cudaStream_t st
         std::lock_guard<std::mutex> lk(g_tc_mu);
         if (first_use_on_current_device(&g_tc_devs) != 0) {          // function attributes are per device
             DANET_CUDA(cudaDeviceGetAttribute(&g_sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
-            DANET_CUDA(cudaFuncSetAttribute(k_conv_tc<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-            DANET_CUDA(cudaFuncSetAttribute(k_conv_tc<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-            DANET_CUDA(cudaFuncSetAttribute(k_conv_tc<true, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+            DANET_CUDA(cudaFuncSetAttribute(k_conv_tc<false, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+            DANET_CUDA(cudaFuncSetAttribute(k_conv_tc<false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+            DANET_CUDA(cudaFuncSetAttribute(k_conv_tc<false, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+            DANET_CUDA(cudaFuncSetAttribute(k_conv_tc<false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+            DANET_CUDA(cudaFuncSetAttribute(k_conv_tc<true, -1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
             g_use_pdl = env_int("DANET_TC_PDL", 1) != 0;
             DANET_CUDA(cudaMalloc((void**)&g_sched[dev], kSchedSlots * 2 * sizeof(unsigned)));
             DANET_CUDA(cudaMemset(g_sched[dev], 0, kSchedSlots * 2 * sizeof(unsigned)));
@@ -1057,14 +1060,16 @@ int conv_tc_group_launch(int n, const danet_conv_problem* probs, cudaStream_t st
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = g_use_pdl ? 1 : 0;
-    int n_exact = 0, n_big = 0;
-    for (int i = 0; i < a.nprob; ++i) { n_exact += a.p[i].exact; n_big += a.p[i].big; }
+    int n_exact = 0, n_big = 0, n_resf = 0;
+    for (int i = 0; i < a.nprob; ++i) { n_exact += a.p[i].exact; n_big += a.p[i].big; n_resf += a.p[i].res_f != nullptr; }
     if (a.prof || a.variant || (n_exact != 0 && (n_exact != a.nprob || n_big != 0))) {
-        DANET_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<true, -1>, a));      // instrumentation / knock-outs / mixed modes: the generic instantiation
+        DANET_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<true, -1, true>, a));      // instrumentation / knock-outs / mixed modes: the generic instantiation
     } else if (n_exact) {
-        DANET_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<false, 1>, a));
+        if (n_resf) { DANET_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<false, 1, true>, a)); }
+        else { DANET_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<false, 1, false>, a)); }
     } else {
-        DANET_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<false, 0>, a));
+        if (n_resf) { DANET_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<false, 0, true>, a)); }
+        else { DANET_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<false, 0, false>, a)); }
     }
     DANET_LAUNCH_CHECK();
     return 0;

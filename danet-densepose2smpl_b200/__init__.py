@@ -8,5 +8,5 @@ from .renderer import IUV_Renderer  # noqa: F401
 from . import geometry, iuvmap  # noqa: F401
 from .danet import DaNet, build_synthetic_danet  # noqa: F401
 from . import synthetic  # noqa: F401
-from . import parallel, evaluate  # noqa: F401
+from . import parallel, evaluate, losses  # noqa: F401
 from .part_utils import PartRenderer  # noqa: F401

@@ -63,6 +63,9 @@ SIGNATURES = {
     "danet_batch_rodrigues": (c_int, [c_int, c_p, c_p, c_int, c_p]),
     "danet_perspective_projection": (c_int, [c_int, c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "danet_mpjpe_h36m": (c_int, [c_int, c_p, c_p, c_p, c_p]),
+    "danet_body_uv_losses_workspace_bytes": (c_i64, [c_int, c_int]),
+    "danet_body_uv_losses": (c_int, [c_int, c_int, c_int, c_int, c_i64, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
+                                     c_p, c_f, c_f, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "danet_raster_create": (c_int, [ctypes.POINTER(RasterDesc), ctypes.POINTER(c_p)]),
     "danet_raster_destroy": (c_int, [c_p]),
     "danet_raster_workspace_bytes": (c_i64, [c_p, c_int]),

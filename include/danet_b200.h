@@ -97,6 +97,26 @@ int danet_mpjpe_h36m(int32_t B, const float* pred_j17, const float* gt_j14, floa
                      danet_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Dense IUV losses of the training step, forward and backward in one pass.
+ * Replaces models/danet/iuv_estimator.py:304-341 (IUV_Estimator.body_uv_losses) and the autograd
+ * graph torch records for it.  Predictions u/v/index [N,C,HW] and targets U/V/I [N,C,HW] (fp32,
+ * channel stride HW, image strides `pred_stride` / `map_stride` in elements, 0 = dense C*HW), optional
+ * annotation logits / targets [N,Cann,HW] (dense, both NULL to skip), optional has_iuv [N] (uint8, NULL =
+ * every image).  losses[4] = { point_weight/batch_size * sum smooth_l1(u - U | I > 0), the same for v,
+ * mean cross-entropy(index, argmax I), mean cross-entropy(ann, argmax Ann) } over the images with
+ * has_iuv (all zero when none has).  grad_* (NULL to skip; laid out like the predictions) receive
+ * d losses[k] / d prediction.  The 24 per-part calls of iuv_estimator.py:232-255 are one call over the
+ * (batch, part)-flattened axis: N = 24 B, batch_size = 24 B, strides 3*7*HW, has_iuv repeated per part.
+ * Deterministic (fixed summation order). */
+int64_t danet_body_uv_losses_workspace_bytes(int32_t N, int32_t HW);
+int danet_body_uv_losses(int32_t N, int32_t C, int32_t Cann, int32_t HW, int64_t pred_stride, int64_t map_stride,
+                         const float* u_pred, const float* v_pred, const float* index_pred, const float* ann_pred,
+                         const float* Umap, const float* Vmap, const float* Imap, const float* Annmap,
+                         const uint8_t* has_iuv, float batch_size, float point_weight, float* losses,
+                         float* grad_u, float* grad_v, float* grad_index, float* grad_ann, void* workspace,
+                         danet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * IUV rasteriser.  Replaces utils/renderer.py:207-298 (IUV_Renderer) and the third-party
  * neural_renderer forward pass it calls; optionally fuses utils/iuvmap.py:103-151 (iuv_img2map).
  * ------------------------------------------------------------------------------------------ */

@@ -1,7 +1,7 @@
 """Generates tests/golden/*.npz by running the REFERENCE'S OWN Python code (imported from
 /root/reference with the shims in oracle/ref_import.py).  Run in this container only:
 
-    python -m oracle.gen_golden [geometry] [iuvmap] [part_utils] [net]
+    python -m oracle.gen_golden [geometry] [iuvmap] [part_utils] [losses] [net]
 
 The vectors pin the oracle restatements (oracle/lbs.py geometry helpers) and the CUDA kernels."""
 import os
@@ -80,10 +80,59 @@ def gen_part_utils(ns):
     print("part_utils.npz written")
 
 
+def gen_losses(ns):
+    """models/danet/iuv_estimator.py:304-341 (body_uv_losses) under torch autograd, and the 24-part loop of
+    iuv_estimator.py:232-255 (here 4 parts of 7 channels): losses and gradients w.r.t. the predictions."""
+    torch = ns.torch
+    F = torch.nn.functional
+    g = torch.Generator().manual_seed(2718)
+    B, C, CA, S, P, CP = 3, 25, 15, 6, 4, 7
+    fn = ns.IUV_Estimator.body_uv_losses                         # `self` is unused apart from the module-level cfg
+
+    def onehot(n, shape):
+        return F.one_hot(torch.randint(0, n, shape, generator=g), n).movedim(-1, -3).float()
+
+    out = {}
+    u, v, i = (torch.randn(B, C, S, S, generator=g).mul_(1.5).requires_grad_() for _ in range(3))
+    a = torch.randn(B, CA, S, S, generator=g).requires_grad_()
+    I = onehot(C, (B, S, S))
+    U, V = torch.rand(B, C, S, S, generator=g) * I, torch.rand(B, C, S, S, generator=g) * I
+    A = onehot(CA, (B, S, S))
+    wts = torch.tensor([1.0, 2.0, 3.0, 4.0])
+    for tag, has in (("all", None), ("some", torch.tensor([True, False, True]))):
+        for t in (u, v, i, a):
+            t.grad = None
+        L = fn(None, u, v, i, a, [U, V, I, A], has)
+        sum(w * l for w, l in zip(wts, L)).backward()
+        out["L_" + tag] = torch.stack([l.detach() for l in L]).numpy()
+        for k, t in (("u", u), ("v", v), ("i", i), ("a", a)):       # gradient of sum_k (k+1) loss_k
+            out["g%s_%s" % (k, tag)] = t.grad.numpy().copy()
+    L = fn(None, u, v, i, a, [U, V, I, A], torch.tensor([False, False, False]))
+    out["L_none"] = torch.stack([l.reshape(()) for l in L]).numpy()
+    out.update(u=u.detach().numpy(), v=v.detach().numpy(), i=i.detach().numpy(), a=a.detach().numpy(),
+               U=U.numpy(), V=V.numpy(), I=I.numpy(), A=A.numpy(), has_some=np.array([1, 0, 1], np.uint8),
+               grad_weights=wts.numpy())
+    # the per-part loop (iuv_estimator.py:232-255), no annotation head
+    pp = torch.randn(B, P, 3, CP, S, S, generator=g).requires_grad_()
+    pI = onehot(CP, (B, P, S, S))
+    pg = torch.stack([torch.rand(B, P, CP, S, S, generator=g) * pI, torch.rand(B, P, CP, S, S, generator=g) * pI, pI], dim=2)
+    has = torch.tensor([True, True, False])
+    tot = None
+    for k in range(P):
+        Lk = fn(None, pp[:, k, 0], pp[:, k, 1], pp[:, k, 2], None, [pg[:, k, 0], pg[:, k, 1], pg[:, k, 2], None], has)[:3]
+        tot = list(Lk) if tot is None else [x + y for x, y in zip(tot, Lk)]
+    tot = [x / float(P) for x in tot]
+    sum(w * l for w, l in zip(wts[:3], tot)).backward()
+    out.update(part_pred=pp.detach().numpy(), part_gt=pg.numpy(), part_has=has.numpy().astype(np.uint8),
+               part_L=torch.stack([l.detach() for l in tot]).numpy(), part_grad=pp.grad.numpy())
+    np.savez_compressed(os.path.join(GOLD, "losses.npz"), **out)
+    print("losses.npz written")
+
+
 def main():
     sys.path.insert(0, ROOT)
     from oracle import ref_import
-    what = sys.argv[1:] or ["geometry", "iuvmap", "part_utils", "net"]
+    what = sys.argv[1:] or ["geometry", "iuvmap", "part_utils", "losses", "net"]
     ns = ref_import.load(48)
     os.makedirs(GOLD, exist_ok=True)
     if "geometry" in what:
@@ -92,6 +141,8 @@ def main():
         gen_iuvmap(ns)
     if "part_utils" in what:
         gen_part_utils(ns)
+    if "losses" in what:
+        gen_losses(ns)
     if "net" in what:
         from oracle import gen_golden_net
         gen_golden_net.main(ns)

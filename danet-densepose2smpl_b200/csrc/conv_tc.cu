@@ -81,7 +81,9 @@ struct alignas(64) Prob {
 constexpr int kMaxProb = 6;
 struct ArgsN {
     int nprob, total_tiles, na_stages, a_slot_bytes, nb_stages, b_slot_bytes;
-    int variant, pad_;                   // bring-up knock-outs (DANET_TC_VARIANT): 1 no stores, 2 no residual/bias loads, 4 no MMAs
+    int variant;                         // bring-up knock-outs (DANET_TC_VARIANT): 1 no stores, 2 no residual/bias loads, 4 no MMAs
+    int mma_order;                       // exact mode, one sub-tile: 1 = per weight block all hi*[hi|lo] MMAs, then all lo*hi MMAs
+                                         // (two same-shape accumulate chains); 0 = alternate per K step (DANET_TC_MMAORDER)
     long long* prof;                     // bring-up: per-role wait cycles of CTA 0 (danet_conv_tc_set_profile_buffer), else NULL
     unsigned* sched;                     // [2]: dynamic tile counter, finished-CTA counter (self-resetting); NULL = static round-robin
     Prob p[kMaxProb];
@@ -574,6 +576,25 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
                         tc_fence_after();
                         const uint64_t bd = bd0 + ((sB + bs * a.b_slot_bytes) >> 4);
                         if (elect_one()) {
+                            if (EX != 0 && exact && !S2 && a.mma_order) {
+                                // One accumulator chain per CTA (N tiles of 96 / 128 channels): alternating the two MMA shapes
+                                // per K step makes every MMA wait for the previous one on the shared columns [NT, 2 NT).
+                                // Issued as two same-shape chains per weight block, consecutive MMAs stream through the
+                                // accumulator like a plain GEMM main loop; the sums are the same products in another order.
+                                const int nt_ = (PROF && (a.variant & 4)) ? 0 : ntk;
+                                for (int tt = 0; tt < nt_; ++tt) {
+                                    const uint32_t toff = (uint32_t)P.tapoff16[slot][k0 + tt];
+                                    for (int kk = 0; kk < kv; ++kk) {
+                                        tc_mma_f16(d_base, ad_hi + toff + 2 * kk, bd + tt * tap16 + 2 * kk, idesc2, acc);
+                                        acc = 1;
+                                    }
+                                }
+                                for (int tt = 0; tt < nt_; ++tt) {
+                                    const uint32_t toff = (uint32_t)P.tapoff16[slot][k0 + tt];
+                                    for (int kk = 0; kk < kv; ++kk)
+                                        tc_mma_f16(d_base + NT, ad_lo + toff + 2 * kk, bd + tt * tap16 + 2 * kk, idesc1, 1u);
+                                }
+                            } else
                             for (int tt = 0; tt < ((PROF && (a.variant & 4)) ? 0 : ntk); ++tt) {
                                 const uint32_t toff = (uint32_t)P.tapoff16[slot][k0 + tt];
                                 for (int kk = 0; kk < kv; ++kk) {
@@ -1029,6 +1050,7 @@ int conv_tc_group_launch(int n, const danet_conv_problem* probs, cudaStream_t st
     }
     a.total_tiles = base;
     a.variant = env_int("DANET_TC_VARIANT", 0);
+    a.mma_order = env_int("DANET_TC_MMAORDER", 1);
     a.prof = g_tc_prof;
     int dev = 0;
     DANET_CUDA(cudaGetDevice(&dev));

@@ -1,6 +1,6 @@
 """Per-layer timing of the tensor-core convolution engine on the layer classes that make up the DaNet step
 (B = 64, HRNet-W48), through the C ABI.  Usage: python tools/tc_layers.py [tag]
-Env: DANET_TC_S, DANET_TC_VARIANT (knock-outs), DANET_TC_NCONCAT, DANET_TC_SWB."""
+Env: DANET_TC_S, DANET_TC_VARIANT (knock-outs), DANET_TC_MMAORDER, DANET_TC_SWB.  Usage: tc_layers.py [tag] [exact|fast] [s1]"""
 import os
 import sys
 
@@ -63,6 +63,9 @@ if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else ""
     if len(sys.argv) > 2:
         MODES = (1,) if sys.argv[2] == "exact" else (0,)
+    if len(sys.argv) > 3 and sys.argv[3] == "s1":
+        # the classes whose exact-mode N tiles (96 / 128 channels) leave one accumulator chain per CTA, + one 48-channel control
+        LAYERS = [l for l in LAYERS if l[0][4] in (96, 192, 384, 128, 256) and l[0][5] == 3 and l[0][6] == 1] + [LAYERS[0]]
     tot = {0: 0.0, 1: 0.0}
     print("# %s S=%s variant=%s" % (tag, os.environ.get("DANET_TC_S", "2"), os.environ.get("DANET_TC_VARIANT", "0")))
     for case, cnt in LAYERS:

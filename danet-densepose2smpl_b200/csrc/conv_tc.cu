@@ -62,6 +62,9 @@ struct alignas(64) Prob {
     int NT, ntn;                         // output channels per N tile, N tiles
     int nconcat;                         // exact mode: hi and lo weight rows share one block (one MMA of width 2*NT)
     int ACC;                             // accumulator columns per sub-tile
+    int mo;                              // MMA issue order inside a weight block: 1 = all hi*[hi|lo] MMAs, then all lo*hi MMAs (two
+                                         // same-shape accumulate chains); 0 = alternating per K step.  A function of the layer's
+                                         // channel count alone, so that an image's bits do not depend on the batch it is in
     int big;                             // S*ACC > 256: the tile takes both accumulator halves
     int nstack, hs, box_h;               // small maps: nstack images share one tile; image n's rows start at group n*hs
                                          // (hs = H + pad: the zero rows between images are the TMA out-of-bounds fill)
@@ -81,9 +84,7 @@ struct alignas(64) Prob {
 constexpr int kMaxProb = 6;
 struct ArgsN {
     int nprob, total_tiles, na_stages, a_slot_bytes, nb_stages, b_slot_bytes;
-    int variant;                         // bring-up knock-outs (DANET_TC_VARIANT): 1 no stores, 2 no residual/bias loads, 4 no MMAs
-    int mma_order;                       // exact mode, one sub-tile: 1 = per weight block all hi*[hi|lo] MMAs, then all lo*hi MMAs
-                                         // (two same-shape accumulate chains); 0 = alternate per K step (DANET_TC_MMAORDER)
+    int variant, pad_;                   // bring-up knock-outs (DANET_TC_VARIANT): 1 no stores, 2 no residual/bias loads, 4 no MMAs
     long long* prof;                     // bring-up: per-role wait cycles of CTA 0 (danet_conv_tc_set_profile_buffer), else NULL
     unsigned* sched;                     // [2]: dynamic tile counter, finished-CTA counter (self-resetting); NULL = static round-robin
     Prob p[kMaxProb];
@@ -119,6 +120,13 @@ static bool make_prob(const danet_conv_desc* d, int S_req, Prob* g) {
     }
     g->nconcat = g->exact;
     g->ACC = g->NT * (g->nconcat ? 2 : 1);
+    // Exact-mode N tiles of more than 64 channels never pair sub-tiles (2 * ACC > 256 columns), whatever the batch: one
+    // accumulator chain per CTA.  Alternating the two MMA shapes per K step then makes every MMA wait for the previous
+    // one on the shared columns [NT, 2 NT) (measured: 1.3-1.8x the operand model); issued as two same-shape chains per
+    // weight block they stream like a plain GEMM main loop (192-ch 14x14: 63 -> 51 us, 384-ch 7x7: 66 -> 52 us, step
+    // 23.3 -> 21.3 ms).  Layers that MAY pair sub-tiles keep the alternating order in every tile -- the order of the fp32
+    // sums must not depend on S, which depends on the batch size (profiles/r02_mma_order.txt).
+    g->mo = (g->exact && 2 * g->ACC > 256 && env_int("DANET_TC_MMAORDER", 1)) ? 1 : 0;
     int S = S_req;
     if (g->Wo <= kTileW) S = 1;
     if (g->exact && S * g->ACC > 256) S = 1;        // segmented accumulation wants two accumulator stages
@@ -576,11 +584,9 @@ k_conv_tc(const __grid_constant__ ArgsN a) {
                         tc_fence_after();
                         const uint64_t bd = bd0 + ((sB + bs * a.b_slot_bytes) >> 4);
                         if (elect_one()) {
-                            if (EX != 0 && exact && !S2 && a.mma_order) {
-                                // One accumulator chain per CTA (N tiles of 96 / 128 channels): alternating the two MMA shapes
-                                // per K step makes every MMA wait for the previous one on the shared columns [NT, 2 NT).
-                                // Issued as two same-shape chains per weight block, consecutive MMAs stream through the
-                                // accumulator like a plain GEMM main loop; the sums are the same products in another order.
+                            if (EX != 0 && exact && P.mo) {
+                                // one accumulator chain per CTA (N tiles of 96 / 128 channels, see make_prob): two same-shape
+                                // chains per weight block; the sums are the same products in another order
                                 const int nt_ = (PROF && (a.variant & 4)) ? 0 : ntk;
                                 for (int tt = 0; tt < nt_; ++tt) {
                                     const uint32_t toff = (uint32_t)P.tapoff16[slot][k0 + tt];
@@ -1050,7 +1056,6 @@ int conv_tc_group_launch(int n, const danet_conv_problem* probs, cudaStream_t st
     }
     a.total_tiles = base;
     a.variant = env_int("DANET_TC_VARIANT", 0);
-    a.mma_order = env_int("DANET_TC_MMAORDER", 1);
     a.prof = g_tc_prof;
     int dev = 0;
     DANET_CUDA(cudaGetDevice(&dev));

@@ -12,6 +12,7 @@ Deviation from the reference, stated: when no image has IUV ground truth the ref
 loss after a host synchronisation (`torch.sum(has_iuv) > 0`); here the losses are 0-dim zeros and nothing synchronises
 (the count stays on the device)."""
 import torch
+from torch.autograd.function import once_differentiable
 
 from . import _lib
 
@@ -72,6 +73,7 @@ class _BodyUvLosses(torch.autograd.Function):
         return losses
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g):
         out = []
         for k, t in enumerate(ctx.grads):
@@ -123,6 +125,7 @@ class _PartIuvLosses(torch.autograd.Function):
         return losses[:3]
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g):
         if ctx.grad is None:
             return None, None, None, None

@@ -24,8 +24,10 @@
 //       two 256-column halves used alternately (a tile that needs more than 256 columns takes both).
 //       exact mode with 2*N <= 256: the hi and lo weight rows are concatenated along N, so hi*[hi|lo] is ONE
 //       MMA of width 2N (the A operand is fetched once) and the epilogue adds the two column ranges.
-//   Epilogue: 8 warps, tcgen05.ld.16x256b (a quad of lanes owns one 32-byte sector of a pixel), bias + residual
-//       + ReLU, output as split-fp16 planes and/or fp32.
+//   MMA issue order (exact mode): N tiles above 64 channels (one accumulator chain per CTA) issue, per weight block, all
+//       hi*[hi|lo] MMAs and then all lo*hi MMAs (two same-shape chains); the other layers alternate per K step.
+//   Epilogue: 8 warps, row-per-thread (tcgen05.ld.32x32b.x16: lane = pixel, 16 channels per load); registers initialised
+//       with bias + residual, every K segment added in fp32 round-to-nearest, ReLU, output as split-fp16 planes and/or fp32.
 //   Launch: programmatic dependent launch; every mbarrier wait is bounded (traps instead of hanging).
 #include "common.cuh"
 #include <cuda.h>
@@ -320,18 +322,6 @@ __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
     return pred != 0;
-}
-// 16 lanes x 256 bits, twice (columns +0..7 and +8..15): thread t receives, for i = 0/1,
-// r[4i], r[4i+1] = row t/4, columns 8i + 2*(t%4) + {0,1};  r[4i+2], r[4i+3] = row t/4 + 8, same columns
-// (the mma m16n8 accumulator fragment).  A quad then owns 32 contiguous bytes of a row.
-__device__ __forceinline__ void tc_ld16x256_x2_nowait(uint32_t taddr, float* v) {
-    uint32_t r[8];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-        : "r"(taddr) : "memory");
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 // 32 lanes x 32 bits, 16 columns: thread i of the warp receives TMEM lane (base lane + i), columns 0..15
 __device__ __forceinline__ void tc_ld32x32_x16_nowait(uint32_t taddr, float* v) {

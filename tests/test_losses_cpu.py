@@ -149,3 +149,33 @@ def test_autograd_layer_over_a_test_double_of_the_kernel(gold, hostlib, monkeypa
     np.testing.assert_allclose(L.detach().numpy(), g["part_L"], rtol=3e-6)
     (L * w[:3]).sum().backward()
     np.testing.assert_allclose(pp.grad.numpy(), g["part_grad"], atol=3e-7)
+
+
+def test_kernel_arithmetic_on_host_matches_oracle_on_random_shapes(hostlib):
+    """Shapes the golden does not cover: odd pixel counts, a single channel, C = 25 / 15 heads, padded image strides,
+    soft (non one-hot) target maps with exact ties (first maximum wins), |d| on both sides of the smooth-L1 knee."""
+    rng = np.random.default_rng(11)
+    for (N, C, Ca, H, W, pad) in ((1, 1, 0, 1, 1, 0), (2, 7, 0, 3, 5, 0), (3, 25, 15, 7, 3, 13), (5, 4, 2, 2, 2, 4), (4, 25, 15, 9, 9, 0)):
+        HW = H * W
+        ps, ms = C * HW + pad, C * HW + 2 * pad
+        f = lambda n, stride: rng.normal(0, 1.5, (n, stride)).astype(np.float32)
+        u, v, i = f(N, ps), f(N, ps), f(N, ps) * 2
+        U, V = f(N, ms), f(N, ms)
+        I = np.maximum(f(N, ms), 0)                                    # about half the entries are exactly 0 (masked out)
+        I[:, :HW] = I[:, HW:2 * HW] if C > 1 else I[:, :HW]            # channel 0 ties channel 1: argmax must take channel 0
+        a = f(N, Ca * HW) if Ca else None
+        A = np.abs(f(N, Ca * HW)) if Ca else None
+        has = (rng.random(N) > 0.3).astype(np.uint8)
+        has[0] = 1
+        view = lambda x, stride, c: x[:, :c * HW].reshape(N, c, H, W)
+        Lr, gr = olosses.body_uv_losses(view(u, ps, C), view(v, ps, C), view(i, ps, C), view(a, 0, Ca) if Ca else None,
+                                        [view(U, ms, C), view(V, ms, C), view(I, ms, C), view(A, 0, Ca) if Ca else None], has)
+        gu, gv, gi = np.full_like(u, 7), np.full_like(v, 7), np.full_like(i, 7)
+        ga = np.full_like(a, 7) if Ca else None
+        L = _host_call(hostlib, N, C, Ca, HW, ps, ms, u, v, i, a, U, V, I, A, has, float(N), 0.5, [gu, gv, gi, ga])
+        np.testing.assert_allclose(L, Lr, rtol=5e-6, atol=1e-7)
+        for got, ref, c in ((gu, gr["u"], C), (gv, gr["v"], C), (gi, gr["index"], C)):
+            np.testing.assert_allclose(got[:, :c * HW].reshape(N, c, H, W), ref, atol=2e-7)
+            assert np.all(got[:, c * HW:] == 7)                         # the padding between images is never written
+        if Ca:
+            np.testing.assert_allclose(ga.reshape(N, Ca, H, W), gr["ann"], atol=2e-7)

@@ -117,3 +117,42 @@ def test_reconstruction_error_matches_independent_procrustes():
         hat = sca / (Ac ** 2).sum() * Ac.dot(Rp) + Bm.mean(0)
         want = np.sqrt(((hat - Bm) ** 2).sum(-1)).mean()
         assert abs(reconstruction_error(A[None], Bm[None])[0] - want) < 1e-9
+
+
+def _grad_worker(rank, world, port, tmp):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from danet_b200 import parallel
+    g = torch.Generator().manual_seed(7)
+    shapes = [(64, 3, 3, 3), (64,), (5,), (128, 64, 1, 1), (0,), (13, 512)]
+    params = [torch.nn.Parameter(torch.zeros(s)) for s in shapes]
+    base = [torch.randn(s, generator=g) for s in shapes]
+    for p, b in zip(params, base):
+        p.grad = b * (rank + 1)                       # rank r contributes (r + 1) * base
+    params[2].grad = None                             # a parameter without a gradient is skipped on every rank
+    half = torch.nn.Parameter(torch.zeros(7, dtype=torch.float64))
+    half.grad = torch.full((7,), float(rank + 1), dtype=torch.float64)      # another dtype: its own bucket
+    n = parallel.all_reduce_gradients(params + [half], bucket_bytes=40000)
+    if rank == 0:
+        torch.save({"n": n, "grads": [None if p.grad is None else p.grad.clone() for p in params], "half": half.grad.clone(),
+                    "base": base}, tmp)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_all_reduce(tmp_path):
+    """Training-step exchange: bucketed all-reduce = mean over ranks, tensor by tensor."""
+    from danet_b200 import parallel
+    out = str(tmp_path / "grads.pt")
+    mp.spawn(_grad_worker, args=(2, 29547, out), nprocs=2, join=True)
+    r = torch.load(out)
+    assert r["n"] >= 3                                # 40 KB buckets split the ~70 KB of fp32 gradients; fp64 gets its own
+    for got, b in zip(r["grads"], r["base"]):
+        if got is None:
+            continue
+        assert torch.allclose(got, b * 1.5, rtol=1e-6, atol=1e-7)            # mean of 1x and 2x
+    assert r["grads"][2] is None
+    assert torch.equal(r["half"], torch.full((7,), 1.5, dtype=torch.float64))
+    assert parallel.all_reduce_gradients([torch.nn.Parameter(torch.zeros(3))]) == 0      # no process group: nothing to do
